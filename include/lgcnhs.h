@@ -1,0 +1,247 @@
+/*
+ * lgcnhs.h — C ABI of the B200-native LGCNHS hot path (liblgcnhs.so).
+ *
+ * The reference (Alex-McAvoy/LGCNHS) is pure Python and has no FFI of its own; the
+ * boundary it exposes is the Python module surface model/LightGCN, model/SpreadMethod,
+ * model/SpreadLightGCN(Opti).  Every entry point below replaces one or
+ * more *library calls* the reference makes from those modules; the reference file:line
+ * each one stands in for is cited next to it.  The Python host code under
+ * light-graph-..._b200/{lgcnhs_b200,model,utils,metrics} binds these with ctypes
+ * (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types; every pointer is a DEVICE pointer unless
+ *     the parameter name ends in _host;
+ *   - the library never allocates or frees caller-visible memory: callers pass
+ *     workspaces sized by the *_workspace_bytes queries;
+ *   - every call is stream-ordered on `stream` (a cudaStream_t passed as void*),
+ *     returns 0 on success or a negative lgc_status, never throws;
+ *   - lgc_last_error_string() gives the thread-local message of the last failure.
+ */
+#ifndef LGCNHS_H_
+#define LGCNHS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* lgc_stream_t; /* cudaStream_t */
+
+enum lgc_status {
+  LGC_OK = 0,
+  LGC_ERR_INVALID = -1,   /* bad argument (shape, alignment, null) */
+  LGC_ERR_CUDA = -2,      /* a CUDA runtime / driver call failed    */
+  LGC_ERR_WORKSPACE = -3, /* workspace too small                     */
+  LGC_ERR_UNSUPPORTED = -4
+};
+
+int lgc_abi_version(void);
+const char* lgc_last_error_string(void);
+/* Number of kernels this library has launched since load / since the last reset
+ * (bench.py's "gpu_launches"). */
+int64_t lgc_launch_count(void);
+void lgc_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * (P1) Graph normalisation, once per graph.
+ * Replaces torch_geometric gcn_norm(edge_index, add_self_loops=False) called at
+ * model/LightGCN/model.py:53 (and LightGCNOpti/model.py:65) on EVERY forward, plus the
+ * COO layout produced by utils/graph.py:12-35.
+ *   src = edge_index[0] (message source,  x_j),  dst = edge_index[1] (aggregation target)
+ *   deg[c]  = #{e : dst[e]==c}          dinv = deg^-1/2 (0 where deg==0)
+ *   val[e]  = dinv[src[e]] * dinv[dst[e]]       (two fp32 factors multiplied, as PyG does)
+ * Output is a CSR keyed by target row: rowptr[n_nodes+1], colidx[nnz] = sources in
+ * ascending order (the order the reference's CPU scatter_add visits them), val[nnz].
+ * Rows longer than LGC_LONG_ROW are additionally listed as fixed-size chunks
+ * (chunk_row/chunk_start, at most lgc_csr_max_chunks(nnz) of them) so that the SpMM can
+ * split them over several CTAs; *n_chunks_host receives the count (one D2H sync).
+ * ---------------------------------------------------------------------------------- */
+#define LGC_LONG_ROW 256   /* rows with more non-zeros than this go to the chunk path */
+#define LGC_CHUNK 1024     /* non-zeros per long-row chunk (one CTA)                  */
+
+int64_t lgc_csr_max_chunks(int64_t nnz);
+int lgc_csr_build_workspace_bytes(int64_t nnz, int64_t n_nodes, size_t* bytes_host);
+int lgc_csr_build(const int64_t* src, const int64_t* dst, int64_t nnz, int64_t n_nodes,
+                  int32_t* rowptr, int32_t* colidx, float* val, float* dinv,
+                  int32_t* chunk_row, int32_t* chunk_start, int32_t* row_chunk_base,
+                  int32_t* n_chunks_host, void* workspace, size_t workspace_bytes,
+                  lgc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * (P2/P3) One propagation layer, fused with the running layer sum.
+ * Replaces MessagePassing.propagate + message (model/LightGCN/model.py:61-63, 76-84:
+ * index_select -> norm*x_j -> scatter_add) and one term of the stack/mean at :66-69.
+ *   Y[r,:] = alpha * ( sum_{e in row r} val[e] * X[colidx[e],:]  +  beta * X0[r,:] )
+ * X, X0, Y are (n_nodes, dim) fp32 row-major, dim in {32, 64, 128}.  X0 may be null when
+ * beta == 0.  Deterministic (fixed summation order, no float atomics).
+ * `partial` is scratch of lgc_csr_max_chunks(nnz)*dim floats, `counters` is n_nodes
+ * int32 that must be zero on entry (the kernel leaves them zero).
+ * row_begin/row_end restrict the launch to a row range (multi-GPU row partition);
+ * chunk_begin/chunk_end = row_chunk_base[row_begin], row_chunk_base[row_end] are the
+ * long-row chunks of that range ([0, n_chunks) for the whole graph).
+ * ---------------------------------------------------------------------------------- */
+int lgc_spmm_layer(const int32_t* rowptr, const int32_t* colidx, const float* val,
+                   const int32_t* chunk_row, const int32_t* chunk_start,
+                   const int32_t* row_chunk_base, int32_t chunk_begin, int32_t chunk_end,
+                   int64_t n_nodes, int32_t dim, int64_t row_begin, int64_t row_end,
+                   const float* X, const float* X0, float alpha, float beta, float* Y,
+                   float* partial, int32_t* counters, lgc_stream_t stream);
+
+/* K-layer forward with the uniform layer mean in Horner form
+ *   S_0 = X0,  S_{l+1} = A_hat S_l + X0,  E = S_K / (K+1)
+ * == mean(stack([X0, A X0, ..., A^K X0])) of model/LightGCN/model.py:56-69.
+ * tmp0/tmp1 are (n_nodes, dim) scratch; E may alias neither. */
+int lgc_propagate_mean(const int32_t* rowptr, const int32_t* colidx, const float* val,
+                       const int32_t* chunk_row, const int32_t* chunk_start,
+                       const int32_t* row_chunk_base, int32_t n_chunks,
+                       int64_t n_nodes, int32_t dim, int32_t n_layers,
+                       const float* X0, float* E, float* tmp0, float* tmp1,
+                       float* partial, int32_t* counters, lgc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * (P6/P4) BPR loss, forward (+ optional backward with embedding-gradient scatter).
+ * Replaces BPRLoss (model/LightGCN/loss.py:12-44) and the six row gathers of
+ * model/LightGCN/train.py:55-57.  Reference quirks kept: loss = -mean(softplus(s+ - s-))
+ * + eps * sum_b(|u0|^2 + |p0|^2 + |n0|^2)  (softplus threshold 20 as torch).
+ *   E, X0        (n_users+n_items, dim) fp32, users first
+ *   users/pos/neg  int64[batch]; pos/neg are ITEM ids (0-based, offset by n_users inside)
+ *   loss_out     float[2]: {total loss, bpr term}
+ *   gE, gX0      optional (n_nodes, dim) fp32, ACCUMULATED into (caller zero-fills)
+ *   scratch      float[lgc_bpr_scratch_floats(batch)], scratch[0] zero on first use
+ *                (the kernel leaves it zero)
+ * ---------------------------------------------------------------------------------- */
+int64_t lgc_bpr_scratch_floats(int64_t batch);
+int lgc_bpr_fwd_bwd(const float* E, const float* X0, int64_t n_users, int64_t n_items,
+                    int32_t dim, const int64_t* users, const int64_t* pos,
+                    const int64_t* neg, int64_t batch, float eps, float grad_scale,
+                    float* loss_out, float* gE, float* gX0, float* scratch,
+                    lgc_stream_t stream);
+
+/* Same loss on six PRE-GATHERED (batch, dim) row blocks — the literal signature of
+ * BPRLoss(users_emb_final, users_emb_0, pos_final, pos_0, neg_final, neg_0, lambda)
+ * (model/LightGCN/loss.py:12).  Gradients (optional, all six or none) are stored, not
+ * accumulated. */
+int lgc_bpr_rows(const float* uf, const float* u0, const float* pf, const float* p0,
+                 const float* nf, const float* n0, int64_t batch, int32_t dim, float eps,
+                 float grad_scale, float* loss_out, float* guf, float* gu0, float* gpf,
+                 float* gp0, float* gnf, float* gn0, float* scratch, lgc_stream_t stream);
+
+/* (P7) Adam step, torch.optim.Adam(lr, betas=(b1,b2), eps) semantics
+ * (model/LightGCN/train.py:104,144): bias corrections are passed pre-computed
+ * (bc1 = 1-b1^t, bc2_sqrt = sqrt(1-b2^t)). */
+int lgc_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                  int64_t n, float lr, float beta1, float beta2, float eps, float bc1,
+                  float bc2_sqrt, lgc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * (P8) score = Xu . Xi^T  (+ optional seen-pair fill), materialised for a block of
+ * users.  Replaces torch.matmul(user_embedding, item_embedding.T) and
+ * score[users, items] = -1024 (model/LightGCN/recommend.py:86,101,111;
+ * evaluation.py:34,49; SpreadLightGCN/model.py:77,92,102).
+ *   out[(u-u0), i] for u in [u0,u1), ld = ldo floats.
+ *   seen_ptr/seen_idx: CSR over ALL users of seen item ids (may be null -> no fill).
+ * ---------------------------------------------------------------------------------- */
+int lgc_score_block(const float* Xu, const float* Xi, int64_t u0, int64_t u1,
+                    int64_t n_items, int32_t dim, const int32_t* seen_ptr,
+                    const int32_t* seen_idx, float fill, float* out, int64_t ldo,
+                    lgc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * (P8/S4) Row-wise masked top-k.  Replaces torch.topk(score, k)
+ * (model/LightGCN/recommend.py:114) and the argsort + Python filter loop of
+ * model/SpreadMethod/recommend.py:35-47 (== SpreadLightGCN/recommend.py:34-46).
+ *   S: (n_rows, n_cols) fp32, ld = lds.  Row r corresponds to user row_offset + r of
+ *   the exclusion CSR (excl_ptr/excl_idx, may be null).  Excluded entries can never be
+ *   selected.  Result sorted by value descending, ties -> larger index first (what the
+ *   CPU reference produces for np.argsort(row)[::-1]).
+ *   out_idx int64 (n_rows, k), out_val fp32 (n_rows, k) or null.  k <= 128, k <= n_cols.
+ * ---------------------------------------------------------------------------------- */
+int lgc_topk_rows(const float* S, int64_t n_rows, int64_t n_cols, int64_t lds,
+                  const int32_t* excl_ptr, const int32_t* excl_idx, int64_t row_offset,
+                  int32_t k, int64_t* out_idx, float* out_val, lgc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * (S0/S1) Hybrid spreading, operand packing.
+ * Replaces the dense float64 A of utils/trans.py:13-29 as GEMM operand.
+ * Input is the interaction list (user, item) int32 of length nnz, duplicates allowed.
+ *   ku[u], ki[i] (float, optional outputs) = degrees of the *deduplicated* matrix.
+ * hs_pack_a:  A  (n_users x ldk) bf16 0/1, K-major for F = A.W   (ldk >= n_items, %64==0)
+ * hs_pack_at: At (n_items x ldk) uint8 0/1 and `digits` planes Q_d (n_items x ldk) uint8
+ *             with Q_d[i,u] = digit_d(q_u) * A[u,i],  q_u = round(2^shift / k_u),
+ *             q_u = sum_d digit_d * 256^d   (exact fixed-point 1/k_u; ldk >= n_users, %128==0)
+ * All outputs must be zero-filled by the caller before the call.
+ * ---------------------------------------------------------------------------------- */
+int hs_degrees(const int32_t* users, const int32_t* items, int64_t nnz, int64_t n_users,
+               int64_t n_items, int32_t* ku, int32_t* ki, uint8_t* dedup_bitmap,
+               lgc_stream_t stream);
+int hs_pack_a(const int32_t* users, const int32_t* items, int64_t nnz, int64_t n_users,
+              int64_t n_items, uint16_t* A_bf16, int64_t ldk, lgc_stream_t stream);
+int hs_pack_at(const int32_t* users, const int32_t* items, int64_t nnz, int64_t n_users,
+               int64_t n_items, const int32_t* ku, int32_t shift, int32_t digits,
+               uint8_t* At_u8, uint8_t* Q_u8, int64_t ldk, int64_t plane_stride,
+               lgc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * (S1/S3) tcgen05 / TMEM tensor-core GEMM on a binary left operand:
+ *     C[m, n] = rs[m] * cs[n] * scale * sum_p w_p * sum_k A[m,k] * B_p[n,k]
+ * A: (M x K) K-major, B_p: `planes` matrices (N x K) K-major, plane stride in elements.
+ * kind 0: bf16 operands, fp32 accumulate, w_p = 1                (planes in {1,2,3})
+ * kind 1: uint8 operands, exact int32 accumulate, w_p = 256^p    (planes in {1,2,4})
+ * Replaces np.dot(A.T / user_degrees, A) (model/SpreadMethod/model.py:25) and
+ * np.dot(F0, W) (model/SpreadMethod/model.py:98).
+ * lda/ldb in elements, multiples of 16 bytes; pointers 16-byte aligned (TMA).
+ * rs / cs may be null (== 1).  C is fp32 row-major (ldc floats).
+ * ---------------------------------------------------------------------------------- */
+int hs_gemm_planes(int32_t kind, const void* A, int64_t lda, const void* B, int64_t ldb,
+                   int64_t plane_stride, int32_t planes, int64_t M, int64_t N, int64_t K,
+                   float* C, int64_t ldc, const float* rs, const float* cs, double scale,
+                   lgc_stream_t stream);
+/* Plain CUDA-core fp32-accumulate version of the same contract, used by the GPU tests as
+ * an on-device cross-check of the tcgen05 path (never by the product path). */
+int hs_gemm_planes_simt(int32_t kind, const void* A, int64_t lda, const void* B,
+                        int64_t ldb, int64_t plane_stride, int32_t planes, int64_t M,
+                        int64_t N, int64_t K, float* C, int64_t ldc, const float* rs,
+                        const float* cs, double scale, lgc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * (S2) HybridS degree scaling:  W[i,j] = G[i,j] / den,  den = k_i^(1-lambda) * k_j^lambda,
+ * den == 0 -> 1  (model/SpreadMethod/model.py:72-83), evaluated in float64 like the
+ * reference and rounded once to fp32.
+ *   W32   optional (n x ldw) fp32 output (row i = source item)
+ *   Wt_planes optional bf16 planes p=0..planes-1 of W^T: plane[p][j, i] = split_p(W[i,j])
+ *             (hi / mid / lo), (n x ldk) each, K-major operand for F = A.W
+ * ---------------------------------------------------------------------------------- */
+int hs_scale_w(const float* G, int64_t ldg, int64_t n, const int32_t* ki, double lambda,
+               float* W32, int64_t ldw, uint16_t* Wt_planes, int64_t ldk,
+               int64_t plane_stride, int32_t planes, lgc_stream_t stream);
+
+/* (F1) Fusion  F_new = G_score * F  (model/SpreadLightGCN/model.py:151), elementwise,
+ * in place on F. */
+int hs_hadamard(float* F, const float* Gscore, int64_t rows, int64_t cols, int64_t ldf,
+                int64_t ldg, lgc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Multi-GPU support for the fused SpMM + all-gather (rows written straight into every
+ * peer's replica over NVLink): CUDA IPC handle export / import for a device buffer.
+ * ---------------------------------------------------------------------------------- */
+int lgc_ipc_get_handle(void* dptr, uint8_t* handle64_host);
+int lgc_ipc_open_handle(const uint8_t* handle64_host, void** dptr_host);
+int lgc_ipc_close_handle(void* dptr);
+/* Same as lgc_spmm_layer for rows [row_begin,row_end) but every finished row is stored
+ * into n_peers output replicas (peer_Y_host[p] = device pointer valid in this process). */
+int lgc_spmm_layer_bcast(const int32_t* rowptr, const int32_t* colidx, const float* val,
+                         const int32_t* chunk_row, const int32_t* chunk_start,
+                         const int32_t* row_chunk_base, int32_t chunk_begin,
+                         int32_t chunk_end, int64_t n_nodes,
+                         int32_t dim, int64_t row_begin, int64_t row_end, const float* X,
+                         const float* X0, float alpha, float beta,
+                         float* const* peer_Y_host, int32_t n_peers, float* partial,
+                         int32_t* counters, lgc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LGCNHS_H_ */

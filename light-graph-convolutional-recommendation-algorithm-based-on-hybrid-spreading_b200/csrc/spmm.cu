@@ -1,0 +1,309 @@
+// spmm.cu — (P2/P3) one LightGCN propagation layer as a CSR SpMM fused with the running
+// layer sum:   Y = alpha * (A_hat X + beta X0).
+// Stands in for MessagePassing.propagate + message at
+// /root/reference/model/LightGCN/model.py:61-63,76-84 (index_select -> norm*x_j ->
+// scatter_add, three library kernels and a materialised (2E, D) message tensor) and for
+// the stack/mean at :66-69 (Horner form, see lgc_propagate_mean).
+//
+// Mapping (HBM/L2-bound integer+fp32 gather work, no tensor cores):
+//   * an embedding row is DIM fp32 = DIM/4 float4; DIM/4 lanes ("sub-group") own one
+//     gathered row, so a warp keeps 32/(DIM/4) rows in flight per load instruction and
+//     every LDG.128 of a sub-group is one fully used, 128-bit-per-lane coalesced segment;
+//   * the (colidx, val) stream of a row is read coalesced, 32 entries per warp load, with
+//     streaming (evict-first) hints, and broadcast with shuffles — the per-non-zero
+//     metadata is staged in registers, never re-read;
+//   * short rows (<= LGC_LONG_ROW non-zeros): one warp per row; long rows are cut into
+//     LGC_CHUNK-sized chunks, one CTA per chunk; the last CTA of a row (ticket counter)
+//     adds the chunk partials in chunk order, so the result is deterministic — there is no
+//     floating-point atomic anywhere;
+//   * the BCAST variant stores each finished row into every peer's replica (NVLink P2P
+//     stores): the per-layer all-gather of the row-partitioned multi-GPU path is fused into
+//     the SpMM epilogue.
+#include "common.cuh"
+
+namespace lgc {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kThreads = kWarpsPerBlock * 32;
+constexpr int kUnroll = 4;
+constexpr int kMaxPeers = 8;
+
+struct PeerPtrs {
+  float* y[kMaxPeers];
+};
+
+__device__ __forceinline__ float4 ld_row4(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+
+// Sum of val[e] * X[colidx[e], :] over e in [start, end) for one warp.  On return every
+// lane li of every sub-group holds the full sum for columns [4*li, 4*li+4).
+template <int DIM>
+__device__ __forceinline__ float4 warp_gather_sum(const int32_t* __restrict__ colidx,
+                                                  const float* __restrict__ val,
+                                                  const float* __restrict__ X, int start, int end,
+                                                  int lane) {
+  constexpr int LPR = DIM / 4;   // lanes per gathered row
+  constexpr int SUB = 32 / LPR;  // rows in flight per warp-wide load
+  const int sub = lane / LPR, li = lane % LPR;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int base = start; base < end; base += 32) {
+    const int idx = base + lane;
+    int c = 0;
+    float v = 0.f;
+    if (idx < end) {
+      c = __ldcs(colidx + idx);
+      v = __ldcs(val + idx);
+    }
+    const int n = min(32, end - base);
+    for (int j = 0; j < n; j += SUB * kUnroll) {
+      float4 x[kUnroll];
+      float w[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int jj = j + u * SUB + sub;
+        const int cc = __shfl_sync(0xffffffffu, c, jj & 31);
+        const float vv = __shfl_sync(0xffffffffu, v, jj & 31);
+        const bool ok = jj < n;
+        w[u] = ok ? vv : 0.f;
+        x[u] = ok ? ld_row4(X + (size_t)cc * DIM + li * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        acc.x = fmaf(w[u], x[u].x, acc.x);
+        acc.y = fmaf(w[u], x[u].y, acc.y);
+        acc.z = fmaf(w[u], x[u].z, acc.z);
+        acc.w = fmaf(w[u], x[u].w, acc.w);
+      }
+    }
+  }
+#pragma unroll
+  for (int off = LPR; off < 32; off <<= 1) {
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off);
+    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
+  }
+  return acc;
+}
+
+template <int NPEER>
+__device__ __forceinline__ void store_row4(float* Y, const PeerPtrs& peers, size_t off, float4 v) {
+  if (NPEER == 0) {
+    *reinterpret_cast<float4*>(Y + off) = v;
+  } else {
+#pragma unroll
+    for (int p = 0; p < kMaxPeers; ++p)
+      if (p < NPEER) *reinterpret_cast<float4*>(peers.y[p] + off) = v;
+  }
+}
+
+template <int DIM, int NPEER>
+__global__ void __launch_bounds__(kThreads)
+spmm_layer_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                  const float* __restrict__ val, const int32_t* __restrict__ chunk_row,
+                  const int32_t* __restrict__ chunk_start, const int32_t* __restrict__ row_chunk_base,
+                  int chunk_begin, int n_chunk_blocks, int row_begin, int row_end,
+                  const float* __restrict__ X, const float* __restrict__ X0, float alpha, float beta,
+                  float* __restrict__ Y, PeerPtrs peers, float* __restrict__ partial,
+                  int32_t* __restrict__ counters, int n_peers_rt) {
+  constexpr int LPR = DIM / 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  (void)n_peers_rt;
+
+  if ((int)blockIdx.x >= n_chunk_blocks) {
+    // ---------------- short rows: one warp per row ----------------
+    const int row = row_begin + ((int)blockIdx.x - n_chunk_blocks) * kWarpsPerBlock + warp;
+    if (row >= row_end) return;
+    const int start = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+    if (end - start > LGC_LONG_ROW) return;  // handled by the chunk CTAs
+    float4 acc = warp_gather_sum<DIM>(colidx, val, X, start, end, lane);
+    if (lane < LPR) {
+      const size_t off = (size_t)row * DIM + lane * 4;
+      if (beta != 0.f) {
+        const float4 x0 = ld_row4(X0 + off);
+        acc.x = fmaf(beta, x0.x, acc.x);
+        acc.y = fmaf(beta, x0.y, acc.y);
+        acc.z = fmaf(beta, x0.z, acc.z);
+        acc.w = fmaf(beta, x0.w, acc.w);
+      }
+      acc.x *= alpha; acc.y *= alpha; acc.z *= alpha; acc.w *= alpha;
+      store_row4<NPEER>(Y, peers, off, acc);
+    }
+    return;
+  }
+
+  // ---------------- long rows: one CTA per LGC_CHUNK non-zeros ----------------
+  __shared__ float s_part[kWarpsPerBlock][DIM];
+  __shared__ int s_last;
+  const int chunk = chunk_begin + (int)blockIdx.x;
+  const int row = __ldg(chunk_row + chunk);
+  const int cstart = __ldg(chunk_start + chunk);
+  const int rstart = __ldg(rowptr + row), rend = __ldg(rowptr + row + 1);
+  const int cend = min(cstart + LGC_CHUNK, rend);
+  constexpr int PER_WARP = LGC_CHUNK / kWarpsPerBlock;
+  const int wstart = min(cstart + warp * PER_WARP, cend), wend = min(wstart + PER_WARP, cend);
+  float4 acc = warp_gather_sum<DIM>(colidx, val, X, wstart, wend, lane);
+  if (lane < LPR) *reinterpret_cast<float4*>(&s_part[warp][lane * 4]) = acc;
+  __syncthreads();
+  const int nch = (rend - rstart + LGC_CHUNK - 1) / LGC_CHUNK;
+  const int chunk0 = __ldg(row_chunk_base + row);
+  float sum = 0.f;
+  if (threadIdx.x < DIM) {
+#pragma unroll
+    for (int w = 0; w < kWarpsPerBlock; ++w) sum += s_part[w][threadIdx.x];
+  }
+  if (nch > 1) {
+    if (threadIdx.x < DIM) {
+      __stcg(partial + (size_t)chunk * DIM + threadIdx.x, sum);
+      __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int ticket = atomicAdd(counters + row, 1);
+      s_last = (ticket == nch - 1);
+      if (s_last) counters[row] = 0;  // leave the counters clean for the next launch
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x < DIM) {
+      sum = 0.f;
+      for (int c = 0; c < nch; ++c) sum += __ldcg(partial + (size_t)(chunk0 + c) * DIM + threadIdx.x);
+    }
+  }
+  if (threadIdx.x < DIM) {
+    const size_t off = (size_t)row * DIM + threadIdx.x;
+    if (beta != 0.f) sum = fmaf(beta, __ldg(X0 + off), sum);
+    sum *= alpha;
+    if (NPEER == 0) {
+      Y[off] = sum;
+    } else {
+#pragma unroll
+      for (int p = 0; p < kMaxPeers; ++p)
+        if (p < NPEER) peers.y[p][off] = sum;
+    }
+  }
+}
+
+template <int NPEER>
+static int launch_spmm(const int32_t* rowptr, const int32_t* colidx, const float* val,
+                       const int32_t* chunk_row, const int32_t* chunk_start,
+                       const int32_t* row_chunk_base, int chunk_begin, int chunk_end,
+                       int64_t row_begin, int64_t row_end, int dim, const float* X, const float* X0,
+                       float alpha, float beta, float* Y, const PeerPtrs& peers, float* partial,
+                       int32_t* counters, cudaStream_t stream) {
+  const int n_chunk_blocks = chunk_end - chunk_begin;
+  const int64_t n_rows = row_end - row_begin;
+  const int64_t grid = n_chunk_blocks + ceil_div(n_rows, kWarpsPerBlock);
+  if (grid == 0) return LGC_OK;
+#define LGC_SPMM_LAUNCH(D)                                                                        \
+  spmm_layer_kernel<D, NPEER><<<(unsigned)grid, kThreads, 0, stream>>>(                           \
+      rowptr, colidx, val, chunk_row, chunk_start, row_chunk_base, chunk_begin, n_chunk_blocks,   \
+      (int)row_begin, (int)row_end, X, X0, alpha, beta, Y, peers, partial, counters, NPEER)
+  switch (dim) {
+    case 32: LGC_SPMM_LAUNCH(32); break;
+    case 64: LGC_SPMM_LAUNCH(64); break;
+    case 128: LGC_SPMM_LAUNCH(128); break;
+    default: LGC_FAIL(LGC_ERR_UNSUPPORTED, "spmm: embedding dim %d not in {32,64,128}", dim);
+  }
+#undef LGC_SPMM_LAUNCH
+  LGC_LAUNCH_CHECK("spmm_layer_kernel");
+  return LGC_OK;
+}
+
+static int check_spmm_args(const int32_t* rowptr, const int32_t* colidx, const float* val,
+                           const int32_t* chunk_row, const int32_t* chunk_start,
+                           const int32_t* row_chunk_base, int chunk_begin, int chunk_end,
+                           int64_t n_nodes, int64_t row_begin, int64_t row_end, const float* X,
+                           const float* X0, float beta, float* partial, int32_t* counters) {
+  LGC_REQUIRE(rowptr && X, "spmm: null rowptr / X");
+  LGC_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= n_nodes, "spmm: bad row range");
+  LGC_REQUIRE(0 <= chunk_begin && chunk_begin <= chunk_end, "spmm: bad chunk range");
+  LGC_REQUIRE(chunk_end == chunk_begin || (chunk_row && chunk_start && row_chunk_base && partial && counters),
+              "spmm: chunk list given without chunk arrays / scratch");
+  LGC_REQUIRE(beta == 0.f || X0, "spmm: beta != 0 needs X0");
+  LGC_REQUIRE(((uintptr_t)X & 15) == 0 && ((uintptr_t)X0 & 15) == 0, "spmm: X / X0 must be 16-byte aligned");
+  (void)colidx; (void)val;
+  return LGC_OK;
+}
+
+}  // namespace lgc
+
+using namespace lgc;
+
+extern "C" int lgc_spmm_layer(const int32_t* rowptr, const int32_t* colidx, const float* val,
+                              const int32_t* chunk_row, const int32_t* chunk_start,
+                              const int32_t* row_chunk_base, int32_t chunk_begin, int32_t chunk_end,
+                              int64_t n_nodes, int32_t dim, int64_t row_begin, int64_t row_end,
+                              const float* X, const float* X0, float alpha, float beta, float* Y,
+                              float* partial, int32_t* counters, lgc_stream_t stream) {
+  int rc = check_spmm_args(rowptr, colidx, val, chunk_row, chunk_start, row_chunk_base, chunk_begin,
+                           chunk_end, n_nodes, row_begin, row_end, X, X0, beta, partial, counters);
+  if (rc) return rc;
+  LGC_REQUIRE(Y && ((uintptr_t)Y & 15) == 0, "spmm: Y null or misaligned");
+  PeerPtrs none{};
+  return launch_spmm<0>(rowptr, colidx, val, chunk_row, chunk_start, row_chunk_base, chunk_begin,
+                        chunk_end, row_begin, row_end, dim, X, X0, alpha, beta, Y, none, partial,
+                        counters, (cudaStream_t)stream);
+}
+
+extern "C" int lgc_spmm_layer_bcast(const int32_t* rowptr, const int32_t* colidx, const float* val,
+                                    const int32_t* chunk_row, const int32_t* chunk_start,
+                                    const int32_t* row_chunk_base, int32_t chunk_begin,
+                                    int32_t chunk_end, int64_t n_nodes, int32_t dim,
+                                    int64_t row_begin, int64_t row_end, const float* X,
+                                    const float* X0, float alpha, float beta,
+                                    float* const* peer_Y_host, int32_t n_peers, float* partial,
+                                    int32_t* counters, lgc_stream_t stream) {
+  int rc = check_spmm_args(rowptr, colidx, val, chunk_row, chunk_start, row_chunk_base, chunk_begin,
+                           chunk_end, n_nodes, row_begin, row_end, X, X0, beta, partial, counters);
+  if (rc) return rc;
+  LGC_REQUIRE(peer_Y_host && n_peers >= 1 && n_peers <= kMaxPeers, "spmm bcast: 1..8 peers");
+  PeerPtrs peers{};
+  for (int p = 0; p < n_peers; ++p) {
+    LGC_REQUIRE(peer_Y_host[p] && ((uintptr_t)peer_Y_host[p] & 15) == 0, "spmm bcast: bad peer pointer");
+    peers.y[p] = peer_Y_host[p];
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+#define LGC_BCAST(NP)                                                                              \
+  case NP:                                                                                         \
+    return launch_spmm<NP>(rowptr, colidx, val, chunk_row, chunk_start, row_chunk_base,            \
+                           chunk_begin, chunk_end, row_begin, row_end, dim, X, X0, alpha, beta,    \
+                           nullptr, peers, partial, counters, s)
+  switch (n_peers) {
+    LGC_BCAST(1); LGC_BCAST(2); LGC_BCAST(3); LGC_BCAST(4);
+    LGC_BCAST(5); LGC_BCAST(6); LGC_BCAST(7); LGC_BCAST(8);
+  }
+#undef LGC_BCAST
+  return LGC_ERR_INVALID;
+}
+
+extern "C" int lgc_propagate_mean(const int32_t* rowptr, const int32_t* colidx, const float* val,
+                                  const int32_t* chunk_row, const int32_t* chunk_start,
+                                  const int32_t* row_chunk_base, int32_t n_chunks, int64_t n_nodes,
+                                  int32_t dim, int32_t n_layers, const float* X0, float* E,
+                                  float* tmp0, float* tmp1, float* partial, int32_t* counters,
+                                  lgc_stream_t stream) {
+  LGC_REQUIRE(X0 && E && n_layers >= 0, "propagate_mean: bad arguments");
+  if (n_layers == 0) {
+    LGC_CUDA(cudaMemcpyAsync(E, X0, sizeof(float) * (size_t)n_nodes * dim, cudaMemcpyDeviceToDevice,
+                             (cudaStream_t)stream));
+    return LGC_OK;
+  }
+  LGC_REQUIRE(n_layers == 1 || (tmp0 && (n_layers == 2 || tmp1)), "propagate_mean: scratch buffers missing");
+  // Horner: S_{l+1} = A S_l + X0, E = S_K / (K+1).  The last layer writes E directly.
+  const float* cur = X0;
+  float* bufs[2] = {tmp0, tmp1};
+  for (int l = 0; l < n_layers; ++l) {
+    const bool last = (l == n_layers - 1);
+    float* out = last ? E : bufs[l & 1];
+    const float alpha = last ? 1.0f / (float)(n_layers + 1) : 1.0f;
+    int rc = lgc_spmm_layer(rowptr, colidx, val, chunk_row, chunk_start, row_chunk_base, 0, n_chunks,
+                            n_nodes, dim, 0, n_nodes, cur, X0, alpha, 1.0f, out, partial, counters,
+                            stream);
+    if (rc) return rc;
+    cur = out;
+  }
+  return LGC_OK;
+}

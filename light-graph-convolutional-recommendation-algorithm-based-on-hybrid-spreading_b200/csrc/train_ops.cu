@@ -1,0 +1,237 @@
+// train_ops.cu — (P4/P6/P7) the per-step training math around the propagation:
+//   * fused BPR forward + backward with the six embedding-row gathers and the
+//     embedding-gradient scatter folded in, standing in for
+//     /root/reference/model/LightGCN/loss.py:12-44 (BPRLoss, ~12 library kernels) and
+//     /root/reference/model/LightGCN/train.py:55-57 (six index_select) plus their autograd
+//     backward (index_add / elementwise);
+//   * Adam, standing in for torch.optim.Adam.step at
+//     /root/reference/model/LightGCN/train.py:104,144.
+// Both are tiny HBM-bound elementwise passes (3.1 MB at B=1024, 7*N*4D bytes for Adam).
+#include "common.cuh"
+
+namespace lgc {
+
+constexpr int kBprThreads = 256;
+constexpr int kBprMaxGrid = 2048;
+
+struct BprPtrs {
+  const float *uf, *u0, *pf, *p0, *nf, *n0;  // row bases (forward operands)
+  float *guf, *gu0, *gpf, *gp0, *gnf, *gn0;  // gradient bases (null -> forward only)
+  const int64_t *iu, *ip, *in;               // row indices, null -> row b (pre-gathered rows)
+};
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float dot4(float4 a, float4 b) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+template <bool ATOMIC>
+__device__ __forceinline__ void add4(float* p, float4 v) {
+  if (ATOMIC) {
+    atomicAdd(p + 0, v.x); atomicAdd(p + 1, v.y); atomicAdd(p + 2, v.z); atomicAdd(p + 3, v.w);
+  } else {
+    *reinterpret_cast<float4*>(p) = v;
+  }
+}
+
+// torch.nn.functional.softplus(x) with beta=1, threshold=20 and its derivative
+__device__ __forceinline__ float softplus_t(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float softplus_grad_t(float x) {
+  if (x > 20.f) return 1.f;
+  const float z = expf(x);
+  return z / (z + 1.f);
+}
+
+// One sub-group of DIM/4 lanes per (user, pos, neg) triplet.
+//   ATOMIC: gradients are scatter-added (duplicate rows in a batch); otherwise stored.
+template <int DIM, bool ATOMIC>
+__global__ void __launch_bounds__(kBprThreads)
+bpr_kernel(BprPtrs P, int64_t batch, float eps, float grad_scale, float* __restrict__ loss_out,
+           float* __restrict__ scratch) {
+  constexpr int LPR = DIM / 4;
+  constexpr int TPB = kBprThreads / LPR;  // triplets per block per pass
+  const int sub = threadIdx.x / LPR, li = threadIdx.x % LPR;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float sp_sum = 0.f, reg_sum = 0.f;
+  const float inv_b = 1.0f / (float)batch;
+
+  for (int64_t b0 = (int64_t)blockIdx.x * TPB; b0 < batch; b0 += (int64_t)gridDim.x * TPB) {
+    const int64_t b = b0 + sub;
+    const bool ok = b < batch;
+    float4 uf = make_float4(0, 0, 0, 0), pf = uf, nf = uf, u0 = uf, p0 = uf, n0 = uf;
+    size_t ou = 0, op = 0, on = 0;
+    if (ok) {
+      ou = (size_t)(P.iu ? P.iu[b] : b) * DIM + li * 4;
+      op = (size_t)(P.ip ? P.ip[b] : b) * DIM + li * 4;
+      on = (size_t)(P.in ? P.in[b] : b) * DIM + li * 4;
+      uf = ld4(P.uf + ou); pf = ld4(P.pf + op); nf = ld4(P.nf + on);
+      u0 = ld4(P.u0 + ou); p0 = ld4(P.p0 + op); n0 = ld4(P.n0 + on);
+    }
+    float sp = dot4(uf, pf), sn = dot4(uf, nf);
+    float rg = dot4(u0, u0) + dot4(p0, p0) + dot4(n0, n0);
+#pragma unroll
+    for (int off = LPR / 2; off >= 1; off >>= 1) {
+      sp += __shfl_xor_sync(0xffffffffu, sp, off);
+      sn += __shfl_xor_sync(0xffffffffu, sn, off);
+      rg += __shfl_xor_sync(0xffffffffu, rg, off);
+    }
+    const float x = sp - sn;
+    if (ok && li == 0) {
+      sp_sum += softplus_t(x);
+      reg_sum += rg;
+    }
+    if (P.guf != nullptr && ok) {
+      // d loss / d x_b = -(1/B) * softplus'(x_b)
+      const float g = -grad_scale * inv_b * softplus_grad_t(x);
+      const float r = 2.f * eps * grad_scale;
+      add4<ATOMIC>(P.guf + ou, make_float4(g * (pf.x - nf.x), g * (pf.y - nf.y), g * (pf.z - nf.z), g * (pf.w - nf.w)));
+      add4<ATOMIC>(P.gpf + op, make_float4(g * uf.x, g * uf.y, g * uf.z, g * uf.w));
+      add4<ATOMIC>(P.gnf + on, make_float4(-g * uf.x, -g * uf.y, -g * uf.z, -g * uf.w));
+      add4<ATOMIC>(P.gu0 + ou, make_float4(r * u0.x, r * u0.y, r * u0.z, r * u0.w));
+      add4<ATOMIC>(P.gp0 + op, make_float4(r * p0.x, r * p0.y, r * p0.z, r * p0.w));
+      add4<ATOMIC>(P.gn0 + on, make_float4(r * n0.x, r * n0.y, r * n0.z, r * n0.w));
+    }
+  }
+
+  // block reduce (fixed order), then the last block adds the block partials in block order
+  __shared__ float s_sp[kBprThreads / 32], s_rg[kBprThreads / 32];
+  __shared__ int s_last;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    sp_sum += __shfl_xor_sync(0xffffffffu, sp_sum, off);
+    reg_sum += __shfl_xor_sync(0xffffffffu, reg_sum, off);
+  }
+  if (lane == 0) { s_sp[warp] = sp_sum; s_rg[warp] = reg_sum; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, c = 0.f;
+    for (int w = 0; w < kBprThreads / 32; ++w) { a += s_sp[w]; c += s_rg[w]; }
+    float* part = scratch + 2;
+    __stcg(part + 2 * blockIdx.x, a);
+    __stcg(part + 2 * blockIdx.x + 1, c);
+    __threadfence();
+    const int ticket = atomicAdd(reinterpret_cast<int*>(scratch), 1);
+    s_last = (ticket == (int)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    float a = 0.f, c = 0.f;
+    const float* part = scratch + 2;
+    for (unsigned i = 0; i < gridDim.x; ++i) { a += __ldcg(part + 2 * i); c += __ldcg(part + 2 * i + 1); }
+    const float bpr = -a * inv_b;
+    loss_out[0] = bpr + eps * c;
+    loss_out[1] = bpr;
+    *reinterpret_cast<int*>(scratch) = 0;
+  }
+}
+
+static int bpr_grid(int64_t batch, int dim) {
+  const int tpb = kBprThreads / (dim / 4);
+  int64_t g = ceil_div(batch, tpb);
+  int64_t cap = (int64_t)num_sms() * 8;
+  if (cap > kBprMaxGrid) cap = kBprMaxGrid;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+template <bool ATOMIC>
+static int launch_bpr(const BprPtrs& P, int dim, int64_t batch, float eps, float grad_scale,
+                      float* loss_out, float* scratch, cudaStream_t stream) {
+  const int grid = bpr_grid(batch, dim);
+  switch (dim) {
+    case 32: bpr_kernel<32, ATOMIC><<<grid, kBprThreads, 0, stream>>>(P, batch, eps, grad_scale, loss_out, scratch); break;
+    case 64: bpr_kernel<64, ATOMIC><<<grid, kBprThreads, 0, stream>>>(P, batch, eps, grad_scale, loss_out, scratch); break;
+    case 128: bpr_kernel<128, ATOMIC><<<grid, kBprThreads, 0, stream>>>(P, batch, eps, grad_scale, loss_out, scratch); break;
+    default: LGC_FAIL(LGC_ERR_UNSUPPORTED, "bpr: embedding dim %d not in {32,64,128}", dim);
+  }
+  LGC_LAUNCH_CHECK("bpr_kernel");
+  return LGC_OK;
+}
+
+__global__ void adam_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
+                            float4* __restrict__ v, int64_t n4, float* __restrict__ pt,
+                            const float* __restrict__ gt, float* __restrict__ mt, float* __restrict__ vt,
+                            int tail, float beta1, float beta2, float eps, float step_size, float bc2_sqrt) {
+  auto upd = [&](float& pp, float gg, float& mm, float& vv) {
+    mm = mm + (gg - mm) * (1.f - beta1);          // exp_avg.lerp_(grad, 1-beta1)
+    vv = vv * beta2 + (1.f - beta2) * gg * gg;    // exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2)
+    const float denom = sqrtf(vv) / bc2_sqrt + eps;
+    pp = pp - step_size * (mm / denom);           // param.addcdiv_(exp_avg, denom, -step_size)
+  };
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
+    upd(pp.x, gg.x, mm.x, vv.x); upd(pp.y, gg.y, mm.y, vv.y);
+    upd(pp.z, gg.z, mm.z, vv.z); upd(pp.w, gg.w, mm.w, vv.w);
+    p[i] = pp; m[i] = mm; v[i] = vv;
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < tail) {
+    const int i = threadIdx.x;
+    float pp = pt[i], mm = mt[i], vv = vt[i];
+    upd(pp, gt[i], mm, vv);
+    pt[i] = pp; mt[i] = mm; vt[i] = vv;
+  }
+}
+
+}  // namespace lgc
+
+using namespace lgc;
+
+extern "C" int64_t lgc_bpr_scratch_floats(int64_t batch) {
+  (void)batch;
+  return 2 + 2 * (int64_t)kBprMaxGrid;  // ticket counter + one (softplus, reg) pair per block
+}
+
+extern "C" int lgc_bpr_fwd_bwd(const float* E, const float* X0, int64_t n_users, int64_t n_items,
+                               int32_t dim, const int64_t* users, const int64_t* pos,
+                               const int64_t* neg, int64_t batch, float eps, float grad_scale,
+                               float* loss_out, float* gE, float* gX0, float* scratch,
+                               lgc_stream_t stream) {
+  LGC_REQUIRE(E && X0 && users && pos && neg && loss_out && scratch, "bpr: null pointer");
+  LGC_REQUIRE(batch > 0 && n_users > 0 && n_items > 0, "bpr: empty batch or tables");
+  LGC_REQUIRE((gE == nullptr) == (gX0 == nullptr), "bpr: gE and gX0 must both be given or both be null");
+  const size_t ioff = (size_t)n_users * dim;
+  BprPtrs P{};
+  P.uf = E; P.pf = E + ioff; P.nf = E + ioff;
+  P.u0 = X0; P.p0 = X0 + ioff; P.n0 = X0 + ioff;
+  if (gE) {
+    P.guf = gE; P.gpf = gE + ioff; P.gnf = gE + ioff;
+    P.gu0 = gX0; P.gp0 = gX0 + ioff; P.gn0 = gX0 + ioff;
+  }
+  P.iu = users; P.ip = pos; P.in = neg;
+  return launch_bpr<true>(P, dim, batch, eps, grad_scale, loss_out, scratch, (cudaStream_t)stream);
+}
+
+extern "C" int lgc_bpr_rows(const float* uf, const float* u0, const float* pf, const float* p0,
+                            const float* nf, const float* n0, int64_t batch, int32_t dim, float eps,
+                            float grad_scale, float* loss_out, float* guf, float* gu0, float* gpf,
+                            float* gp0, float* gnf, float* gn0, float* scratch, lgc_stream_t stream) {
+  LGC_REQUIRE(uf && u0 && pf && p0 && nf && n0 && loss_out && scratch, "bpr rows: null pointer");
+  LGC_REQUIRE(batch > 0, "bpr rows: empty batch");
+  const bool bwd = guf != nullptr;
+  LGC_REQUIRE(!bwd || (gu0 && gpf && gp0 && gnf && gn0), "bpr rows: partial gradient outputs");
+  BprPtrs P{};
+  P.uf = uf; P.u0 = u0; P.pf = pf; P.p0 = p0; P.nf = nf; P.n0 = n0;
+  P.guf = guf; P.gu0 = gu0; P.gpf = gpf; P.gp0 = gp0; P.gnf = gnf; P.gn0 = gn0;
+  return launch_bpr<false>(P, dim, batch, eps, grad_scale, loss_out, scratch, (cudaStream_t)stream);
+}
+
+extern "C" int lgc_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                             int64_t n, float lr, float beta1, float beta2, float eps, float bc1,
+                             float bc2_sqrt, lgc_stream_t stream) {
+  LGC_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0, "adam: null pointer / empty");
+  LGC_REQUIRE((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0,
+              "adam: buffers must be 16-byte aligned");
+  LGC_REQUIRE(bc1 > 0.f && bc2_sqrt > 0.f, "adam: bias corrections must be positive");
+  const int64_t n4 = n / 4;
+  const int tail = (int)(n - n4 * 4);
+  int64_t grid = ceil_div(n4 > 0 ? n4 : 1, 256);
+  const int64_t cap = (int64_t)num_sms() * 16;
+  if (grid > cap) grid = cap;
+  adam_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+      (float4*)param, (const float4*)grad, (float4*)exp_avg, (float4*)exp_avg_sq, n4, param + n4 * 4,
+      grad + n4 * 4, exp_avg + n4 * 4, exp_avg_sq + n4 * 4, tail, beta1, beta2, eps, lr / bc1, bc2_sqrt);
+  LGC_LAUNCH_CHECK("adam_kernel");
+  return LGC_OK;
+}

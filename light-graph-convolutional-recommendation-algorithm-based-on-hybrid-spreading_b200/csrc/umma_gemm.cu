@@ -1,0 +1,461 @@
+// umma_gemm.cu — (S1/S3) the two dense contractions of hybrid spreading on the 5th-gen
+// tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by TMA):
+//     G = A^T K_u^-1 A      /root/reference/model/SpreadMethod/model.py:25   (np.dot, fp64)
+//     F = A W               /root/reference/model/SpreadMethod/model.py:98   (np.dot, fp64)
+// Both have a BINARY (0/1) left operand; the real right operand is carried as `planes`
+// narrow matrices that are multiplied against the same A tile inside ONE MMA:
+//   kind 0 (bf16 x bf16 -> fp32): planes = hi / mid / lo bf16 split of an fp32 matrix; every
+//          product 0/1 x bf16 is exact, the three partial sums live in separate TMEM column
+//          ranges and are added lo-first in the epilogue;
+//   kind 1 (u8 x u8 -> s32): planes = base-256 digits of the fixed-point integer
+//          q_u = round(2^s / k_u); all products and sums are exact integers, the digit sums
+//          are recombined in float64 in the epilogue and rounded once to fp32.
+//
+// Kernel shape (one persistent CTA per SM, 192 threads, warp-specialised):
+//   warp 0      TMA producer  : A tile 128 x 128B and `planes` B tiles NB x 128B per stage
+//                               (SWIZZLE_128B, K-major), 4-stage mbarrier ring
+//   warp 1      MMA issuer    : one thread issues 4 x tcgen05.mma (M=128, N=planes*NB, K=32B)
+//                               per stage into a double-buffered TMEM accumulator (2 x 256 col)
+//   warps 2..5  epilogue      : tcgen05.ld 32x32b -> combine planes -> scale -> fp32 store,
+//                               overlapped with the next tile's main loop
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace lgc {
+namespace umma {
+
+constexpr int kBlockM = 128;
+constexpr int kKBytes = 128;  // bytes of K per stage = one 128B swizzle atom
+constexpr int kStages = 4;
+constexpr int kAStage = kBlockM * kKBytes;  // 16 KB
+constexpr int kBStage = 256 * kKBytes;      // 32 KB (N <= 256 rows)
+constexpr int kStageBytes = kAStage + kBStage;
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 512;
+constexpr int kAccStride = 256;
+constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must trap (sticky CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) {  // ~2 s at 2 GHz
+      printf("lgcnhs umma_gemm: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
+//   start address >> 4 | LBO (unused for swizzled K-major) | SBO = 8 rows * 128 B = 1024 B
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int KIND>
+__device__ __forceinline__ void mma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                       uint32_t accumulate) {
+  if (KIND == 0) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct GemmParams {
+  int64_t M, N;      // output rows, output columns (per plane)
+  int num_kb;        // K blocks of 128 bytes
+  int planes, NB;    // planes and output columns per tile
+  int tiles_m, tiles_n;
+  float* C;
+  int64_t ldc;
+  const float* rs;
+  const float* cs;
+  double scale;
+  int k_elems_per_kb;  // 64 (bf16) or 128 (u8)
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(kThreads, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
+                 const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smemA = smem;
+  uint8_t* smemB = smem + kStages * kAStage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* full = bars;                    // [kStages]
+  uint64_t* empty = bars + kStages;         // [kStages]
+  uint64_t* tfull = bars + 2 * kStages;     // [2]
+  uint64_t* tempty = bars + 2 * kStages + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int n_mma = p.planes * p.NB;  // MMA N
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapB) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      const uint32_t stage_tx = (uint32_t)(kAStage + n_mma * kKBytes);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m_blk = t % p.tiles_m, n_blk = t / p.tiles_m;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], stage_tx);
+          const int k0 = kb * p.k_elems_per_kb;
+          tma_load_2d(&tmapA, &full[stage], smemA + stage * kAStage, k0, m_blk * kBlockM);
+          for (int pl = 0; pl < p.planes; ++pl)
+            tma_load_3d(&tmapB, &full[stage], smemB + stage * kBStage + pl * p.NB * kKBytes, k0,
+                        n_blk * p.NB, pl);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    // instruction descriptor: D fmt | A fmt | B fmt | K-major both | N>>3 | M>>4
+    uint32_t idesc = 0;
+    if (KIND == 0) idesc |= (1u << 4) | (1u << 7) | (1u << 10);  // F32 accum, BF16 x BF16
+    else idesc |= (2u << 4);                                     // S32 accum, U8 x U8 (fmt 0)
+    idesc |= ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * kAccStride;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t adesc = make_smem_desc(smem_u32(smemA + stage * kAStage));
+          const uint64_t bdesc = make_smem_desc(smem_u32(smemB + stage * kBStage));
+#pragma unroll
+          for (int k = 0; k < kKBytes / 32; ++k)  // 32 bytes of K per MMA: +2 in >>4 units
+            mma_ss<KIND>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          tc_commit(&empty[stage]);  // frees the smem stage when these MMAs retire
+          if (kb == p.num_kb - 1) tc_commit(&tfull[acc]);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (warps 2..5) ------------------------------
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int m_blk = t % p.tiles_m, n_blk = t / p.tiles_m;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int64_t row = (int64_t)m_blk * kBlockM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const float rscale = (row_ok && p.rs) ? __ldg(p.rs + row) : 1.0f;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride;
+      float* crow = p.C + (row_ok ? row : 0) * p.ldc;
+      for (int c0 = 0; c0 < p.NB; c0 += 16) {
+        uint32_t r[3][16];
+        float out[16];
+        // digits / split planes are at column offsets pl*NB inside the accumulator
+        tmem_ld16(t_row + c0, r[0]);
+        if (p.planes > 1) tmem_ld16(t_row + p.NB + c0, r[1]);
+        if (p.planes > 2) tmem_ld16(t_row + 2 * p.NB + c0, r[2]);
+        uint32_t r3[16];
+        if (KIND == 1 && p.planes > 3) tmem_ld16(t_row + 3 * p.NB + c0, r3);
+        tmem_ld_wait();
+        const int64_t col0 = (int64_t)n_blk * p.NB + c0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float v;
+          if (KIND == 0) {
+            float a = __uint_as_float(r[0][j]);
+            if (p.planes == 2) a = __uint_as_float(r[1][j]) + a;
+            if (p.planes == 3) a = (__uint_as_float(r[2][j]) + __uint_as_float(r[1][j])) + a;
+            v = a * (float)p.scale;
+          } else {
+            long long tot = (long long)(int)r[0][j];
+            if (p.planes > 1) tot += (long long)(int)r[1][j] << 8;
+            if (p.planes > 2) tot += (long long)(int)r[2][j] << 16;
+            if (p.planes > 3) tot += (long long)(int)r3[j] << 24;
+            v = (float)((double)tot * p.scale);
+          }
+          const int64_t col = col0 + j;
+          const float cscale = (p.cs && col < p.N) ? __ldg(p.cs + col) : 1.0f;
+          out[j] = v * rscale * cscale;
+        }
+        if (row_ok) {
+          if (col0 + 16 <= p.N && (p.ldc & 3) == 0 && ((uintptr_t)p.C & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<float4*>(crow + col0 + j) = make_float4(out[j], out[j + 1], out[j + 2], out[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (col0 + j < p.N) crow[col0 + j] = out[j];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols)
+                 : "memory");
+  }
+}
+
+// ---- host side: tensor maps through the driver entry point (no -lcuda link dependency) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+// naive on-device cross-check (double accumulate), one thread per output
+template <int KIND>
+__global__ void gemm_planes_simt_kernel(const void* A_, int64_t lda, const void* B_, int64_t ldb,
+                                        int64_t plane_stride, int planes, int64_t M, int64_t N, int64_t K,
+                                        float* C, int64_t ldc, const float* rs, const float* cs, double scale) {
+  const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t m = blockIdx.y;
+  if (n >= N || m >= M) return;
+  double tot = 0.0;
+  for (int pl = planes - 1; pl >= 0; --pl) {
+    double s = 0.0;
+    if (KIND == 0) {
+      const uint16_t* A = (const uint16_t*)A_ + m * lda;
+      const uint16_t* B = (const uint16_t*)B_ + pl * plane_stride + n * ldb;
+      for (int64_t k = 0; k < K; ++k)
+        s += (double)__uint_as_float((uint32_t)A[k] << 16) * (double)__uint_as_float((uint32_t)B[k] << 16);
+      tot += s;
+    } else {
+      const uint8_t* A = (const uint8_t*)A_ + m * lda;
+      const uint8_t* B = (const uint8_t*)B_ + pl * plane_stride + n * ldb;
+      long long si = 0;
+      for (int64_t k = 0; k < K; ++k) si += (long long)A[k] * (long long)B[k];
+      tot += (double)si * (double)(1ll << (8 * pl));
+    }
+  }
+  float v = (float)(tot * scale);
+  if (KIND == 0) v = (float)tot * (float)scale;
+  C[m * ldc + n] = v * (rs ? rs[m] : 1.f) * (cs ? cs[n] : 1.f);
+}
+
+static int check_gemm_args(int kind, const void* A, int64_t lda, const void* B, int64_t ldb,
+                           int64_t plane_stride, int planes, int64_t M, int64_t N, int64_t K, float* C,
+                           int64_t ldc) {
+  LGC_REQUIRE(kind == 0 || kind == 1, "gemm: kind must be 0 (bf16) or 1 (u8)");
+  LGC_REQUIRE(A && B && C, "gemm: null pointer");
+  LGC_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem");
+  LGC_REQUIRE(lda >= K && ldb >= K && ldc >= N, "gemm: leading dimension smaller than extent");
+  if (kind == 0) LGC_REQUIRE(planes >= 1 && planes <= 3, "gemm: bf16 kind takes 1..3 planes");
+  else LGC_REQUIRE(planes == 1 || planes == 2 || planes == 4, "gemm: u8 kind takes 1, 2 or 4 planes");
+  LGC_REQUIRE(planes == 1 || plane_stride >= N * ldb, "gemm: plane stride overlaps planes");
+  return LGC_OK;
+}
+
+}  // namespace umma
+}  // namespace lgc
+
+using namespace lgc;
+using namespace lgc::umma;
+
+extern "C" int hs_gemm_planes(int32_t kind, const void* A, int64_t lda, const void* B, int64_t ldb,
+                              int64_t plane_stride, int32_t planes, int64_t M, int64_t N, int64_t K,
+                              float* C, int64_t ldc, const float* rs, const float* cs, double scale,
+                              lgc_stream_t stream_) {
+  int rc = check_gemm_args(kind, A, lda, B, ldb, plane_stride, planes, M, N, K, C, ldc);
+  if (rc) return rc;
+  const int esize = kind == 0 ? 2 : 1;
+  LGC_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "gemm: operands must be 16-byte aligned");
+  LGC_REQUIRE((lda * esize) % 16 == 0 && (ldb * esize) % 16 == 0 && (plane_stride * esize) % 16 == 0,
+              "gemm: leading dimensions / plane stride must be multiples of 16 bytes");
+  LGC_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "gemm: extents exceed int32");
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) LGC_FAIL(LGC_ERR_CUDA, "gemm: cuTensorMapEncodeTiled entry point not available");
+
+  const int NB = planes == 1 ? 256 : planes == 2 ? 128 : planes == 3 ? 80 : 64;
+  const int k_elems = kKBytes / esize;
+  const CUtensorMapDataType dt = kind == 0 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
+    cuuint64_t strides[1] = {(cuuint64_t)lda * esize};
+    cuuint32_t box[2] = {(cuuint32_t)k_elems, (cuuint32_t)kBlockM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&tmA, dt, 2, const_cast<void*>(A), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) LGC_FAIL(LGC_ERR_CUDA, "gemm: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, (cuuint64_t)planes};
+    cuuint64_t strides[2] = {(cuuint64_t)ldb * esize, (cuuint64_t)(planes > 1 ? plane_stride : N * ldb) * esize};
+    cuuint32_t box[3] = {(cuuint32_t)k_elems, (cuuint32_t)NB, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&tmB, dt, 3, const_cast<void*>(B), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) LGC_FAIL(LGC_ERR_CUDA, "gemm: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+  }
+
+  GemmParams p{};
+  p.M = M; p.N = N;
+  p.num_kb = (int)ceil_div(K, k_elems);
+  p.planes = planes; p.NB = NB;
+  p.tiles_m = (int)ceil_div(M, kBlockM);
+  p.tiles_n = (int)ceil_div(N, NB);
+  p.C = C; p.ldc = ldc; p.rs = rs; p.cs = cs; p.scale = scale;
+  p.k_elems_per_kb = k_elems;
+  const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (kind == 0) {
+    static bool attr0 = false;
+    if (!attr0) {
+      LGC_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+      attr0 = true;
+    }
+    umma_gemm_kernel<0><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, p);
+  } else {
+    static bool attr1 = false;
+    if (!attr1) {
+      LGC_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+      attr1 = true;
+    }
+    umma_gemm_kernel<1><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, p);
+  }
+  LGC_LAUNCH_CHECK("umma_gemm_kernel");
+  return LGC_OK;
+}
+
+extern "C" int hs_gemm_planes_simt(int32_t kind, const void* A, int64_t lda, const void* B, int64_t ldb,
+                                   int64_t plane_stride, int32_t planes, int64_t M, int64_t N, int64_t K,
+                                   float* C, int64_t ldc, const float* rs, const float* cs, double scale,
+                                   lgc_stream_t stream) {
+  int rc = check_gemm_args(kind, A, lda, B, ldb, plane_stride, planes, M, N, K, C, ldc);
+  if (rc) return rc;
+  LGC_REQUIRE(M < 65536, "simt gemm: M too large for the cross-check kernel");
+  dim3 grid((unsigned)ceil_div(N, 128), (unsigned)M);
+  if (kind == 0)
+    gemm_planes_simt_kernel<0><<<grid, 128, 0, (cudaStream_t)stream>>>(A, lda, B, ldb, plane_stride, planes, M, N, K,
+                                                                        C, ldc, rs, cs, scale);
+  else
+    gemm_planes_simt_kernel<1><<<grid, 128, 0, (cudaStream_t)stream>>>(A, lda, B, ldb, plane_stride, planes, M, N, K,
+                                                                        C, ldc, rs, cs, scale);
+  LGC_LAUNCH_CHECK("gemm_planes_simt_kernel");
+  return LGC_OK;
+}

@@ -1,0 +1,377 @@
+"""Torch-tensor level wrappers over the C ABI.
+
+torch is used for device memory, streams and (in dist.py) the NCCL process group only;
+every numerical kernel below is a hand-written sm_100a kernel in csrc/.  All functions
+require CUDA tensors and raise on anything else — there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Sequence
+
+import torch
+
+from ._lib import LgcnhsError, check, lib
+
+LONG_ROW = 256
+CHUNK = 1024
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype: torch.dtype, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise LgcnhsError(f"{name}: expected a CUDA tensor (the B200 path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise LgcnhsError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise LgcnhsError(f"{name}: tensor must be contiguous")
+    return t
+
+
+# --------------------------------------------------------------------------------------------
+# (P1-P3) normalised graph + propagation
+# --------------------------------------------------------------------------------------------
+class NormGraph:
+    """D^-1/2 A D^-1/2 in target-keyed CSR, built once per graph (gcn_norm semantics).
+
+    edge_index: (2, nnz) int64 CUDA tensor; row 0 = message source, row 1 = target
+    (model/LightGCN/model.py:53,62 — `propagate(edge_index, x, norm)`, flow source_to_target).
+    """
+
+    def __init__(self, edge_index: torch.Tensor, n_nodes: int):
+        ei = _req(edge_index, torch.int64, "edge_index")
+        if ei.dim() != 2 or ei.shape[0] != 2:
+            raise LgcnhsError("edge_index must have shape (2, nnz)")
+        dev = ei.device
+        self.device = dev
+        self.n_nodes = int(n_nodes)
+        self.nnz = int(ei.shape[1])
+        L = lib()
+        nnz, n = self.nnz, self.n_nodes
+        self.rowptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        self.colidx = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+        self.val = torch.empty(max(nnz, 1), dtype=torch.float32, device=dev)
+        self.dinv = torch.empty(n, dtype=torch.float32, device=dev)
+        max_chunks = int(L.lgc_csr_max_chunks(nnz))
+        self.chunk_row = torch.empty(max_chunks, dtype=torch.int32, device=dev)
+        self.chunk_start = torch.empty(max_chunks, dtype=torch.int32, device=dev)
+        self.row_chunk_base = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        ws_bytes = C.c_size_t(0)
+        check(L.lgc_csr_build_workspace_bytes(nnz, n, C.byref(ws_bytes)), "csr workspace")
+        ws = torch.empty(ws_bytes.value, dtype=torch.uint8, device=dev)
+        n_chunks = C.c_int32(0)
+        src, dst = ei[0], ei[1]
+        check(L.lgc_csr_build(_ptr(src), _ptr(dst), nnz, n, _ptr(self.rowptr), _ptr(self.colidx), _ptr(self.val),
+                              _ptr(self.dinv), _ptr(self.chunk_row), _ptr(self.chunk_start),
+                              _ptr(self.row_chunk_base), C.byref(n_chunks), _ptr(ws), ws_bytes.value, _stream()),
+              "csr build")
+        del ws
+        self.n_chunks = int(n_chunks.value)
+        self.chunk_row = self.chunk_row[: max(self.n_chunks, 1)].clone()
+        self.chunk_start = self.chunk_start[: max(self.n_chunks, 1)].clone()
+        self._scratch: dict[int, tuple[torch.Tensor, torch.Tensor]] = {}
+
+    def _scr(self, dim: int):
+        s = self._scratch.get(dim)
+        if s is None:
+            partial = torch.empty(max(self.n_chunks, 1) * dim, dtype=torch.float32, device=self.device)
+            counters = torch.zeros(self.n_nodes, dtype=torch.int32, device=self.device)
+            s = (partial, counters)
+            self._scratch[dim] = s
+        return s
+
+    def chunk_range(self, row_begin: int, row_end: int) -> tuple[int, int]:
+        if row_begin == 0 and row_end == self.n_nodes:
+            return 0, self.n_chunks
+        b = self.row_chunk_base[[row_begin, row_end]].tolist()
+        return int(b[0]), int(b[1])
+
+    def spmm(self, X: torch.Tensor, X0: Optional[torch.Tensor] = None, alpha: float = 1.0, beta: float = 0.0,
+             out: Optional[torch.Tensor] = None, row_begin: int = 0, row_end: Optional[int] = None,
+             chunks: Optional[tuple[int, int]] = None) -> torch.Tensor:
+        """out[r] = alpha * (sum_e val[e] X[colidx[e]] + beta X0[r]) for r in [row_begin, row_end)."""
+        X = _req(X, torch.float32, "X")
+        n, dim = self.n_nodes, int(X.shape[1])
+        if X.shape[0] != n:
+            raise LgcnhsError(f"X has {X.shape[0]} rows, graph has {n} nodes")
+        if X0 is not None:
+            _req(X0, torch.float32, "X0")
+        if out is None:
+            out = torch.empty_like(X)
+        _req(out, torch.float32, "out")
+        row_end = n if row_end is None else row_end
+        cb, ce = chunks if chunks is not None else self.chunk_range(row_begin, row_end)
+        partial, counters = self._scr(dim)
+        check(lib().lgc_spmm_layer(_ptr(self.rowptr), _ptr(self.colidx), _ptr(self.val), _ptr(self.chunk_row),
+                                   _ptr(self.chunk_start), _ptr(self.row_chunk_base), cb, ce, n, dim, row_begin,
+                                   row_end, _ptr(X), _ptr(X0), float(alpha), float(beta), _ptr(out), _ptr(partial),
+                                   _ptr(counters), _stream()), "spmm layer")
+        return out
+
+    def spmm_bcast(self, X: torch.Tensor, X0: Optional[torch.Tensor], alpha: float, beta: float,
+                   peer_ptrs: Sequence[int], row_begin: int, row_end: int, chunks: tuple[int, int]) -> None:
+        """Row range of one layer, every finished row stored into all peers' replicas."""
+        X = _req(X, torch.float32, "X")
+        n, dim = self.n_nodes, int(X.shape[1])
+        partial, counters = self._scr(dim)
+        arr = (C.c_void_p * len(peer_ptrs))(*[C.c_void_p(p) for p in peer_ptrs])
+        check(lib().lgc_spmm_layer_bcast(_ptr(self.rowptr), _ptr(self.colidx), _ptr(self.val), _ptr(self.chunk_row),
+                                         _ptr(self.chunk_start), _ptr(self.row_chunk_base), chunks[0], chunks[1], n,
+                                         dim, row_begin, row_end, _ptr(X), _ptr(X0), float(alpha), float(beta), arr,
+                                         len(peer_ptrs), _ptr(partial), _ptr(counters), _stream()),
+              "spmm layer bcast")
+
+    def propagate_mean(self, X0: torch.Tensor, n_layers: int, out: Optional[torch.Tensor] = None,
+                       tmp: Optional[tuple[torch.Tensor, torch.Tensor]] = None) -> torch.Tensor:
+        """E = mean_l(A_hat^l X0), l = 0..n_layers (model/LightGCN/model.py:56-69)."""
+        X0 = _req(X0, torch.float32, "X0")
+        n, dim = self.n_nodes, int(X0.shape[1])
+        if X0.shape[0] != n:
+            raise LgcnhsError(f"X0 has {X0.shape[0]} rows, graph has {n} nodes")
+        if out is None:
+            out = torch.empty_like(X0)
+        if tmp is None:
+            tmp = (torch.empty_like(X0), torch.empty_like(X0))
+        partial, counters = self._scr(dim)
+        check(lib().lgc_propagate_mean(_ptr(self.rowptr), _ptr(self.colidx), _ptr(self.val), _ptr(self.chunk_row),
+                                       _ptr(self.chunk_start), _ptr(self.row_chunk_base), self.n_chunks, n, dim,
+                                       int(n_layers), _ptr(X0), _ptr(out), _ptr(tmp[0]), _ptr(tmp[1]), _ptr(partial),
+                                       _ptr(counters), _stream()), "propagate_mean")
+        return out
+
+    # algorithmic bytes of one layer, SURVEY.md §8(d): no-reuse model
+    def layer_bytes(self, dim: int) -> int:
+        return self.nnz * (4 + 4 + 4 * dim) + self.n_nodes * (4 * dim + 4) + 4
+
+    def layer_bytes_compulsory(self, dim: int) -> int:
+        return self.nnz * 8 + (self.n_nodes + 1) * 4 + 2 * self.n_nodes * 4 * dim
+
+
+# --------------------------------------------------------------------------------------------
+# (P4/P6/P7) BPR + Adam
+# --------------------------------------------------------------------------------------------
+_bpr_scratch: dict[torch.device, torch.Tensor] = {}
+
+
+def _bpr_scr(dev: torch.device) -> torch.Tensor:
+    s = _bpr_scratch.get(dev)
+    if s is None:
+        s = torch.zeros(int(lib().lgc_bpr_scratch_floats(0)), dtype=torch.float32, device=dev)
+        _bpr_scratch[dev] = s
+    return s
+
+
+def bpr_fwd_bwd(E: torch.Tensor, X0: torch.Tensor, n_users: int, n_items: int, users: torch.Tensor,
+                pos: torch.Tensor, neg: torch.Tensor, eps: float, gE: Optional[torch.Tensor] = None,
+                gX0: Optional[torch.Tensor] = None, grad_scale: float = 1.0) -> torch.Tensor:
+    """Returns loss_out = [total, bpr]; if gE/gX0 are given the row gradients are scatter-added."""
+    E = _req(E, torch.float32, "E")
+    X0 = _req(X0, torch.float32, "X0")
+    dim = int(E.shape[1])
+    for t, nm in ((users, "users"), (pos, "pos"), (neg, "neg")):
+        _req(t, torch.int64, nm)
+    loss = torch.empty(2, dtype=torch.float32, device=E.device)
+    check(lib().lgc_bpr_fwd_bwd(_ptr(E), _ptr(X0), n_users, n_items, dim, _ptr(users), _ptr(pos), _ptr(neg),
+                                int(users.numel()), float(eps), float(grad_scale), _ptr(loss), _ptr(gE), _ptr(gX0),
+                                _ptr(_bpr_scr(E.device)), _stream()), "bpr")
+    return loss
+
+
+def bpr_rows(rows: Sequence[torch.Tensor], eps: float, grads: Optional[Sequence[torch.Tensor]] = None,
+             grad_scale: float = 1.0) -> torch.Tensor:
+    """rows = (u_f, u_0, p_f, p_0, n_f, n_0), each (B, dim) fp32."""
+    rows = [_req(t, torch.float32, "bpr row block") for t in rows]
+    B, dim = int(rows[0].shape[0]), int(rows[0].shape[1])
+    loss = torch.empty(2, dtype=torch.float32, device=rows[0].device)
+    g = [None] * 6 if grads is None else list(grads)
+    check(lib().lgc_bpr_rows(*[_ptr(t) for t in rows], B, dim, float(eps), float(grad_scale), _ptr(loss),
+                             *[_ptr(t) for t in g], _ptr(_bpr_scr(rows[0].device)), _stream()), "bpr rows")
+    return loss
+
+
+def adam_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: int,
+              lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8) -> None:
+    for t, nm in ((param, "param"), (grad, "grad"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        _req(t, torch.float32, nm)
+    bc1 = 1.0 - beta1 ** step
+    bc2_sqrt = math.sqrt(1.0 - beta2 ** step)
+    check(lib().lgc_adam_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), int(param.numel()), float(lr),
+                              float(beta1), float(beta2), float(eps), float(bc1), float(bc2_sqrt), _stream()), "adam")
+
+
+# --------------------------------------------------------------------------------------------
+# (P8/S4) scores and top-k
+# --------------------------------------------------------------------------------------------
+def score_block(Xu: torch.Tensor, Xi: torch.Tensor, u0: int, u1: int, seen: Optional[tuple] = None,
+                fill: float = -1024.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    Xu = _req(Xu, torch.float32, "Xu")
+    Xi = _req(Xi, torch.float32, "Xi")
+    M, dim = int(Xi.shape[0]), int(Xi.shape[1])
+    if out is None:
+        out = torch.empty((u1 - u0, M), dtype=torch.float32, device=Xu.device)
+    sp, si = (None, None) if seen is None else seen
+    check(lib().lgc_score_block(_ptr(Xu), _ptr(Xi), u0, u1, M, dim, _ptr(sp), _ptr(si), float(fill), _ptr(out),
+                                int(out.stride(0)), _stream()), "score block")
+    return out
+
+
+def topk_rows(S: torch.Tensor, k: int, excl: Optional[tuple] = None, row_offset: int = 0,
+              want_values: bool = True):
+    S = _req(S, torch.float32, "S") if S.is_contiguous() else S
+    if S.dtype != torch.float32 or not S.is_cuda or S.stride(1) != 1:
+        raise LgcnhsError("topk: S must be a CUDA fp32 matrix with unit column stride")
+    rows, cols = int(S.shape[0]), int(S.shape[1])
+    idx = torch.empty((rows, k), dtype=torch.int64, device=S.device)
+    val = torch.empty((rows, k), dtype=torch.float32, device=S.device) if want_values else None
+    ep, ei = (None, None) if excl is None else excl
+    check(lib().lgc_topk_rows(_ptr(S), rows, cols, int(S.stride(0)), _ptr(ep), _ptr(ei), int(row_offset), int(k),
+                              _ptr(idx), _ptr(val), _stream()), "topk rows")
+    return idx, val
+
+
+def seen_csr(users: torch.Tensor, items: torch.Tensor, n_users: int, n_items: int):
+    """(user, item) pairs -> deduplicated int32 CSR (rowptr, item ids ascending) on device."""
+    key = torch.unique(users.to(torch.int64) * n_items + items.to(torch.int64))
+    u = torch.div(key, n_items, rounding_mode="floor")
+    cnt = torch.bincount(u, minlength=n_users)
+    rowptr = torch.zeros(n_users + 1, dtype=torch.int64, device=users.device)
+    torch.cumsum(cnt, 0, out=rowptr[1:])
+    return rowptr.to(torch.int32), (key - u * n_items).to(torch.int32)
+
+
+# --------------------------------------------------------------------------------------------
+# (S1-S3) spreading GEMMs
+# --------------------------------------------------------------------------------------------
+def gemm_planes(kind: int, A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int,
+                out: Optional[torch.Tensor] = None, rs: Optional[torch.Tensor] = None,
+                cs: Optional[torch.Tensor] = None, scale: float = 1.0, simt: bool = False) -> torch.Tensor:
+    """C = rs*cs*scale * sum_p w_p A B_p^T.  A: (M, lda); B: (planes, N, ldb); K-major."""
+    dt = torch.bfloat16 if kind == 0 else torch.uint8
+    for t, nm in ((A, "A"), (B, "B planes")):
+        if not t.is_cuda or t.dtype != dt or t.stride(-1) != 1:
+            raise LgcnhsError(f"{nm}: expected a CUDA {dt} tensor with unit inner stride")
+    if B.dim() != 3 or A.dim() != 2:
+        raise LgcnhsError("A must be (M, lda) and B (planes, N, ldb)")
+    planes = int(B.shape[0])
+    if out is None:
+        ldc = (N + 3) // 4 * 4
+        out = torch.empty((M, ldc), dtype=torch.float32, device=A.device)[:, :N]
+    fn = lib().hs_gemm_planes_simt if simt else lib().hs_gemm_planes
+    check(fn(kind, _ptr(A), int(A.stride(0)), _ptr(B), int(B.stride(1)), int(B.stride(0)), planes, M, N, K,
+             _ptr(out), int(out.stride(0)), _ptr(rs), _ptr(cs), float(scale), _stream()), "gemm planes")
+    return out
+
+
+def _pad(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class SpreadingEngine:
+    """Device-resident hybrid HeatS/ProbS spreading for one interaction matrix A (train ⊕ val).
+
+    Mirrors the call sequence of model/SpreadMethod/recommend.py:81-111:
+        G = getSpreadingGeneralMat(A); W = HybridS(A, G, lambda); F = getResource(A, W);
+        recommendForAllUser(F, ...)
+    with G cached across lambda values (the findLambda.py:81-116 pattern).
+    """
+
+    def __init__(self, n_users: int, n_items: int, users: torch.Tensor, items: torch.Tensor,
+                 w_planes: int = 3, g_kind: str = "u8"):
+        users = _req(users.to(torch.int32).contiguous(), torch.int32, "users")
+        items = _req(items.to(torch.int32).contiguous(), torch.int32, "items")
+        self.U, self.M = int(n_users), int(n_items)
+        self.dev = users.device
+        self.users, self.items = users, items
+        self.nnz = int(users.numel())
+        self.w_planes = int(w_planes)
+        self.g_kind = g_kind
+        L = lib()
+        U, M, dev = self.U, self.M, self.dev
+        self.ku = torch.zeros(U, dtype=torch.int32, device=dev)
+        self.ki = torch.zeros(M, dtype=torch.int32, device=dev)
+        bitmap = torch.zeros((U * M + 31) // 32, dtype=torch.int32, device=dev)
+        check(L.hs_degrees(_ptr(users), _ptr(items), self.nnz, U, M, _ptr(self.ku), _ptr(self.ki), _ptr(bitmap),
+                           _stream()), "degrees")
+        del bitmap
+        self.ldM = _pad(M, 64)   # K extent (items) of A and W^T planes, bf16
+        self.A = torch.zeros((U, self.ldM), dtype=torch.bfloat16, device=dev)
+        check(L.hs_pack_a(_ptr(users), _ptr(items), self.nnz, U, M, _ptr(self.A), self.ldM, _stream()), "pack_a")
+        self.G: Optional[torch.Tensor] = None
+        self.Wt: Optional[torch.Tensor] = None
+        self._excl = None
+
+    # exclusion CSR (train ⊕ val items of every user) for the filtered top-k
+    @property
+    def excl(self):
+        if self._excl is None:
+            self._excl = seen_csr(self.users, self.items, self.U, self.M)
+        return self._excl
+
+    def fixed_point(self) -> tuple[int, int]:
+        """(digits, shift) of the base-256 fixed-point 1/k_u: q_u = round(2^shift / k_u) < 256^digits,
+        relative error <= k_max / 2^(shift+1)."""
+        nz = self.ku[self.ku > 0]
+        kmin, kmax = int(nz.min()), int(nz.max())
+        digits = 4
+        shift = 8 * digits - 1 + int(math.floor(math.log2(kmin)))
+        return digits, shift
+
+    def general_w(self, item_range: Optional[tuple[int, int]] = None) -> torch.Tensor:
+        """G = A^T K_u^-1 A (model/SpreadMethod/model.py:14-27) on the tensor cores."""
+        L = lib()
+        U, M, dev = self.U, self.M, self.dev
+        j0, j1 = (0, M) if item_range is None else item_range
+        if self.g_kind == "u8":
+            ldU = _pad(U, 128)
+            digits, shift = self.fixed_point()
+            At = torch.zeros((M, ldU), dtype=torch.uint8, device=dev)
+            Q = torch.zeros((digits, M, ldU), dtype=torch.uint8, device=dev)
+            check(L.hs_pack_at(_ptr(self.users), _ptr(self.items), self.nnz, U, M, _ptr(self.ku), shift, digits,
+                               _ptr(At), _ptr(Q), ldU, M * ldU, _stream()), "pack_at")
+            G = gemm_planes(1, At, Q[:, j0:j1], M, j1 - j0, U, scale=2.0 ** (-shift))
+        else:
+            raise LgcnhsError("g_kind must be 'u8'")
+        if item_range is None:
+            self.G = G
+        return G
+
+    def scale(self, lam: float, G: Optional[torch.Tensor] = None, want_w32: bool = False):
+        """W = HybridS(A, G, lambda) (model/SpreadMethod/model.py:63-85) -> bf16 planes of W^T (+ fp32 W)."""
+        G = self.G if G is None else G
+        if G is None:
+            raise LgcnhsError("scale(): general_w() has not been computed")
+        M, dev = self.M, self.dev
+        if self.Wt is None:
+            self.Wt = torch.zeros((self.w_planes, M, self.ldM), dtype=torch.bfloat16, device=dev)
+        W32 = torch.empty((M, M), dtype=torch.float32, device=dev) if want_w32 else None
+        check(lib().hs_scale_w(_ptr(G), int(G.stride(0)), M, _ptr(self.ki), float(lam), _ptr(W32), M, _ptr(self.Wt),
+                               self.ldM, M * self.ldM, self.w_planes, _stream()), "scale_w")
+        return W32
+
+    def resource(self, user_range: Optional[tuple[int, int]] = None, out: Optional[torch.Tensor] = None):
+        """F = A . W (model/SpreadMethod/model.py:88-99) for a block of users."""
+        if self.Wt is None:
+            raise LgcnhsError("resource(): scale() has not been called")
+        u0, u1 = (0, self.U) if user_range is None else user_range
+        return gemm_planes(0, self.A[u0:u1], self.Wt, u1 - u0, self.M, self.M, out=out)
+
+    def recommend(self, lam: float, k: int, filtered: bool = True, gscore: Optional[torch.Tensor] = None,
+                  user_range: Optional[tuple[int, int]] = None, F_out: Optional[torch.Tensor] = None):
+        """lambda -> top-k item ids (U, k) int64 + scores; optional fusion F * gscore."""
+        if self.G is None:
+            self.general_w()
+        self.scale(lam)
+        F = self.resource(user_range, out=F_out)
+        u0 = 0 if user_range is None else user_range[0]
+        if gscore is not None:
+            check(lib().hs_hadamard(_ptr(F), _ptr(gscore), int(F.shape[0]), int(F.shape[1]), int(F.stride(0)),
+                                    int(gscore.stride(0)), _stream()), "hadamard")
+        return topk_rows(F, k, self.excl if filtered else None, row_offset=u0)

@@ -1,0 +1,121 @@
+"""GPU parity: (P1-P3) CSR build, SpMM layer, fused K-layer mean vs. the CPU oracle.
+
+Tolerance (north_star): <= 1e-5 relative, stated as
+    |x - ref| <= 1e-5*|ref| + 1e-7*max|ref|   elementwise  (SURVEY.md §8d).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lightgcn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL_REL = 1e-5, 1e-7
+
+
+def assert_close(x, ref, what=""):
+    x = x.detach().cpu().double()
+    ref = ref.detach().cpu().double()
+    tol = RTOL * ref.abs() + ATOL_REL * ref.abs().max()
+    bad = (x - ref).abs() > tol
+    assert not bad.any(), f"{what}: {int(bad.sum())} / {bad.numel()} out of tolerance, max err {(x-ref).abs().max():.3e}"
+
+
+def make_graph(name, hub=0):
+    from lgcnhs_b200.synth import synth_shape, bipartite_adj
+
+    d = synth_shape(name)
+    users, items = d.users, d.items
+    if hub:  # one item connected to `hub` users -> exercises the multi-chunk long-row path
+        hu = np.arange(min(hub, d.n_users))
+        users = np.concatenate([users, hu])
+        items = np.concatenate([items, np.zeros_like(hu)])
+    adj = torch.from_numpy(bipartite_adj(d.n_users, users, items))
+    return d, adj
+
+
+@pytest.mark.parametrize("name,hub", [("tiny", 0), ("small", 300), ("ml-100k", 0), ("ml-100k", 943)])
+def test_csr_matches_gcn_norm(dev, name, hub):
+    from lgcnhs_b200.ops import NormGraph
+
+    d, adj = make_graph(name, hub)
+    n = d.n_users + d.n_items
+    g = NormGraph(adj.to(dev), n)
+    ei, norm = O.gcn_norm(adj)
+    # oracle CSR keyed by target (col), sources ascending
+    order = np.lexsort((adj[0].numpy(), adj[1].numpy()))
+    rowptr = np.zeros(n + 1, dtype=np.int64)
+    np.add.at(rowptr, adj[1].numpy() + 1, 1)
+    rowptr = np.cumsum(rowptr)
+    assert np.array_equal(g.rowptr.cpu().numpy(), rowptr)                       # integer work: bit-exact
+    assert np.array_equal(g.colidx.cpu().numpy()[: adj.shape[1]], adj[0].numpy()[order])
+    assert np.array_equal(g.val.cpu().numpy()[: adj.shape[1]], norm.numpy()[order])  # fp32 bit-exact
+    deg = (rowptr[1:] - rowptr[:-1]).astype(np.float32)
+    with np.errstate(divide="ignore"):
+        dinv = np.where(deg > 0, 1.0 / np.sqrt(deg), 0).astype(np.float32)
+    assert np.array_equal(g.dinv.cpu().numpy(), dinv)
+
+
+@pytest.mark.parametrize("name,hub,dim", [("tiny", 0, 64), ("small", 300, 64), ("ml-100k", 943, 64),
+                                          ("small", 300, 32), ("small", 300, 128)])
+def test_spmm_layer(dev, name, hub, dim):
+    from lgcnhs_b200.ops import NormGraph
+
+    d, adj = make_graph(name, hub)
+    n = d.n_users + d.n_items
+    g = NormGraph(adj.to(dev), n)
+    torch.manual_seed(42)
+    x = torch.randn(n, dim) * 0.1
+    x0 = torch.randn(n, dim) * 0.1
+    ei, norm = O.gcn_norm(adj)
+    ref = O.propagate(ei, x, norm)
+    y = g.spmm(x.to(dev))
+    assert_close(y, ref, "A x")
+    y2 = g.spmm(x.to(dev), x0.to(dev), alpha=0.25, beta=1.0)
+    assert_close(y2, 0.25 * (ref + x0), "alpha (A x + beta x0)")
+    # determinism: bit-identical on a second launch (no float atomics)
+    assert torch.equal(y, g.spmm(x.to(dev)))
+    # row-range launch == the same rows of the full launch
+    r0, r1 = n // 3, 2 * n // 3
+    part = torch.zeros_like(y)
+    g.spmm(x.to(dev), out=part, row_begin=r0, row_end=r1)
+    assert torch.equal(part[r0:r1], y[r0:r1]) and not part[:r0].any() and not part[r1:].any()
+
+
+@pytest.mark.parametrize("name,layers", [("tiny", 3), ("ml-100k", 3), ("small", 1), ("small", 0), ("small", 4)])
+def test_propagate_mean(dev, name, layers):
+    from lgcnhs_b200.ops import NormGraph
+
+    d, adj = make_graph(name, hub=200)
+    n = d.n_users + d.n_items
+    torch.manual_seed(42)
+    uw = torch.empty(d.n_users, 64).normal_(std=0.1)
+    iw = torch.empty(d.n_items, 64).normal_(std=0.1)
+    uf, _, itf, _ = O.lightgcn_forward(uw, iw, adj, layers)
+    g = NormGraph(adj.to(dev), n)
+    E = g.propagate_mean(torch.cat([uw, iw]).to(dev), layers)
+    assert_close(E, torch.cat([uf, itf]), f"mean of {layers} layers")
+
+
+def test_empty_and_isolated_nodes(dev):
+    """Ragged input: nodes without edges (zero degree -> dinv 0, output row 0) and an edgeless graph."""
+    from lgcnhs_b200.ops import NormGraph
+
+    adj = torch.tensor([[0, 5], [5, 0]], dtype=torch.int64)
+    g = NormGraph(adj.to(dev), 8)
+    x = torch.arange(8 * 64, dtype=torch.float32).reshape(8, 64)
+    y = g.spmm(x.to(dev)).cpu()
+    assert torch.equal(y[0], x[5]) and torch.equal(y[5], x[0]) and not y[[1, 2, 3, 4, 6, 7]].any()
+    g0 = NormGraph(torch.zeros((2, 0), dtype=torch.int64, device=dev), 8)
+    assert not g0.spmm(x.to(dev)).any()
+
+
+def test_bad_edges_fail_loudly(dev):
+    from lgcnhs_b200._lib import LgcnhsError
+    from lgcnhs_b200.ops import NormGraph
+
+    with pytest.raises(LgcnhsError):
+        NormGraph(torch.tensor([[0, 9], [9, 0]], dtype=torch.int64, device=dev), 8)
+    with pytest.raises(LgcnhsError):
+        NormGraph(torch.tensor([[0, 1], [1, 0]], dtype=torch.int64), 8)  # CPU tensor: no fallback

@@ -1,0 +1,96 @@
+"""GPU parity: (P8 / S4) score block + seen fill, and row-wise masked top-k.
+
+Top-k ids must be identical except at float ties (north_star), so ids are compared where the
+reference scores are distinct and the score-at-rank everywhere."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lightgcn_oracle as O
+from oracle import spread_oracle as S
+from test_gpu_propagation import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def test_score_block_and_fill(dev):
+    from lgcnhs_b200 import ops
+    from lgcnhs_b200.synth import synth_shape
+
+    d = synth_shape("ml-100k")
+    torch.manual_seed(42)
+    uw = torch.empty(d.n_users, 64).normal_(std=0.1)
+    iw = torch.empty(d.n_items, 64).normal_(std=0.1)
+    tr, va, _ = d.split()
+    e_tr = torch.from_numpy(np.stack([d.users[tr], d.items[tr]]))
+    e_va = torch.from_numpy(np.stack([d.users[va], d.items[va]]))
+    ref = O.masked_score(uw, iw, e_tr, e_va)
+    seen = ops.seen_csr(torch.cat([e_tr[0], e_va[0]]).to(dev), torch.cat([e_tr[1], e_va[1]]).to(dev), d.n_users, d.n_items)
+    out = ops.score_block(uw.to(dev), iw.to(dev), 0, d.n_users, seen)
+    assert_close(out, ref, "masked score")
+    assert (out.cpu() == -1024).sum() == (ref == -1024).sum()
+    # a user sub-block with an odd offset
+    blk = ops.score_block(uw.to(dev), iw.to(dev), 101, 777, seen)
+    assert torch.equal(blk, out[101:777])
+    # P8 end to end: torch.topk(score, k) ids
+    for k in (10, 20, 100):
+        idx, val = ops.topk_rows(out, k)
+        rv, ri = O.topk_items(ref, k)
+        assert_close(val, rv, "top-k scores")
+        distinct = (rv[:, 1:] != rv[:, :-1]).all(dim=1)
+        assert torch.equal(idx.cpu()[distinct], ri[distinct])
+
+
+@pytest.mark.parametrize("rows,cols,k", [(7, 33, 5), (64, 1682, 20), (33, 3706, 100), (5, 26744, 20), (3, 70000, 128),
+                                         (4, 20, 20)])
+def test_topk_rows_random(dev, rows, cols, k):
+    from lgcnhs_b200 import ops
+
+    g = torch.Generator().manual_seed(rows * 1000 + cols)
+    Sm = torch.randn(rows, cols, generator=g)
+    Sm[0, : cols // 2] = 0.0          # heavy ties
+    if rows > 1:
+        Sm[1] = -Sm[1].abs()          # all negative
+    idx, val = ops.topk_rows(Sm.to(dev), k)
+    rv, _ = torch.topk(Sm, k)
+    assert torch.equal(val.cpu(), rv)                       # selection + order are exact
+    assert torch.equal(torch.gather(Sm, 1, idx.cpu()), rv)  # ids point at those values
+    assert all(len(set(r.tolist())) == k for r in idx.cpu())
+
+
+def test_topk_ties_prefer_larger_index(dev):
+    from lgcnhs_b200 import ops
+
+    Sm = torch.zeros(2, 50)
+    Sm[1, 7] = 1.0
+    idx, _ = ops.topk_rows(Sm.to(dev), 3)
+    assert idx.cpu().tolist() == [[49, 48, 47], [7, 49, 48]]   # np.argsort(row)[::-1] order
+
+
+def test_topk_with_exclusion_matches_reference_loop(dev):
+    """S4: argsort + Python filter loop (model/SpreadMethod/recommend.py:35-47)."""
+    from lgcnhs_b200 import ops
+    from lgcnhs_b200.synth import synth_shape
+
+    d = synth_shape("small")
+    g = torch.Generator().manual_seed(3)
+    F = torch.rand(d.n_users, d.n_items, generator=g)
+    F[F < 0.3] = 0.0
+    F = F.double()      # float64 like the reference, but exactly representable in fp32
+    A = S.interaction_matrix(d.n_users, d.n_items, d.users, d.items)
+    seen = {}
+    for u, i in zip(d.users.tolist(), d.items.tolist()):
+        seen.setdefault(u, []).append(i)
+    ref = S.recommend_loop(F.numpy(), seen, 20)
+    excl = ops.seen_csr(torch.from_numpy(d.users).to(dev), torch.from_numpy(d.items).to(dev), d.n_users, d.n_items)
+    F32 = F.float()
+    idx, val = ops.topk_rows(F32.to(dev), 20, excl)
+    idx = idx.cpu().numpy()
+    fi, fv = S.recommend_fast(F32.double().numpy(), A, 20)
+    assert np.array_equal(idx, fi)                               # same rule, vectorised oracle
+    for u in range(d.n_users):
+        r = np.asarray(ref[u])
+        assert not set(idx[u].tolist()) & set(seen.get(u, []))   # never recommends a seen item
+        assert np.array_equal(F.numpy()[u, r].astype(np.float32), val.cpu().numpy()[u])   # score at rank
+        ok = np.r_[True, fv[u][1:] != fv[u][:-1]] & np.r_[fv[u][1:] != fv[u][:-1], True]
+        assert np.array_equal(idx[u][ok], r[ok])                 # ids equal wherever scores are distinct
