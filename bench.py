@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py — the driver-facing benchmark of the LGCNHS hot paths on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (our arm; torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  (reference arm: the reference's CPU
+                                                              algorithm on the box's host cores)
+
+Primary metric (BASELINE.json: "LightGCN prop GB/s (frac of HBM peak)"): one step = one K=3,
+D=64 fused propagation + layer mean over the TRAIN graph of the ML-20M shape
+(138 493 x 26 744, 20 M interactions -> nnz = 32 M) — BASELINE config 5's propagation, the
+largest propagation workload and one that fits a single B200.  value = algorithmic bytes
+(264 B per non-zero + 260 B per node, per layer) / device time.
+With N GPUs the rows are partitioned by nnz; each rank computes its rows and stores them into
+every peer's replica over NVLink inside the SpMM kernel (fused all-gather), one barrier per
+layer.  scaling = "strong" (the graph is fixed).
+
+The same JSON line carries the two other quantities the metric names, measured on BASELINE
+config 2 (ML-1M shape, hybrid spreading, top-20): "spreading": W GEMM TFLOP/s and users/s.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "light-graph-convolutional-recommendation-algorithm-based-on-hybrid-spreading_b200")
+for _p in (PKG, ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+K_LAYERS, DIM = 3, 64
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p["hbm_gbs"], p["bf16_tflops"], p.get("bf16_tflops_sustained", p["bf16_tflops"]), "measured"
+    except Exception:
+        return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# workload construction (synthetic, seeded; cached per box under /tmp)
+# ------------------------------------------------------------------------------------------
+def load_shape(name: str, rank: int = 0, barrier=None):
+    from lgcnhs_b200.synth import Interactions, synth_shape
+
+    path = f"/tmp/lgcnhs_synth_{name}_42.npz"
+    if rank == 0 and not os.path.exists(path):
+        d = synth_shape(name)
+        np.savez(path + ".tmp.npz", users=d.users, items=d.items, n=np.array([d.n_users, d.n_items]))
+        os.replace(path + ".tmp.npz", path)
+    if barrier is not None:
+        barrier()
+    z = np.load(path)
+    return Interactions(int(z["n"][0]), int(z["n"][1]), z["users"], z["items"])
+
+
+def train_adj(d):
+    from lgcnhs_b200.synth import bipartite_adj
+
+    tr, va, te = d.split()
+    return bipartite_adj(d.n_users, d.users[tr], d.items[tr]), (tr, va, te)
+
+
+def prop_bytes(nnz: int, n: int, layers: int = K_LAYERS, dim: int = DIM) -> int:
+    return layers * (nnz * (4 + 4 + 4 * dim) + n * (4 * dim + 4) + 4)
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU algorithm (oracle port; PyG is not installable)
+# ------------------------------------------------------------------------------------------
+def cpu_prop_sample(adj: np.ndarray, n_users: int, n_items: int, steps: int, warmup: int):
+    """One PyG-equivalent propagation layer (gcn_norm + index_select/mul/scatter_add,
+    model/LightGCN/model.py:53,62,84) on the full graph, all host threads."""
+    from oracle import lightgcn_oracle as LO
+
+    ei = torch.from_numpy(adj)
+    torch.manual_seed(42)
+    x = torch.empty(n_users + n_items, DIM).normal_(std=0.1)
+    ts = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        e, norm = LO.gcn_norm(ei)           # the reference recomputes the norm on every forward
+        LO.propagate(e, x, norm)
+        if i >= warmup:
+            ts.append(time.perf_counter() - t0)
+    sec = float(np.mean(ts))
+    return prop_bytes(adj.shape[1], n_users + n_items, layers=1) / sec / 1e9, sec
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    d = load_shape(args.shape)
+    adj, _ = train_adj(d)
+    steps, warmup = max(1, min(args.steps, 3)), 1
+    gbs, sec = cpu_prop_sample(adj, d.n_users, d.n_items, steps, warmup)
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": "LightGCN prop GB/s", "value": round(gbs, 3), "unit": "GB/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": round(sec * 1e3, 3),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"LightGCN propagation D={DIM}, {args.shape} shape train graph "
+                               f"(nnz={adj.shape[1]}, N={d.n_users + d.n_items})"},
+        "cpu_baseline": {"value": round(gbs, 3), "unit": "GB/s", "cores": cores, "kind": "port",
+                         "sample": "1 of 3 propagation layers over the full graph (gcn_norm + index_select + "
+                                   "scatter_add, PyG-equivalent oracle port), algorithmic bytes of 1 layer / time"},
+        "e2e": {"value": round(gbs, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def spreading_leg(dev, steps: int, warmup: int):
+    """BASELINE config 2: ML-1M shape, G once, then per lambda: scale + F = A.W + filtered top-20."""
+    from lgcnhs_b200 import ops
+
+    d = load_shape("ml-1m")
+    tr, va, _ = d.split()
+    sel = np.concatenate([tr, va])
+    users = torch.from_numpy(d.users[sel]).to(dev)
+    items = torch.from_numpy(d.items[sel]).to(dev)
+    eng = ops.SpreadingEngine(d.n_users, d.n_items, users, items)
+    U, M = d.n_users, d.n_items
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+    # G build (int8 tcgen05 GEMM), timed alone
+    eng.general_w()
+    torch.cuda.synchronize()
+    ev[0].record()
+    for _ in range(steps):
+        eng.general_w()
+    ev[1].record()
+    F = torch.empty((U, (M + 3) // 4 * 4), dtype=torch.float32, device=dev)[:, :M]
+    lams = np.linspace(0.0, 1.0, steps + warmup)
+    for lam in lams[:warmup]:
+        eng.recommend(float(lam), 20, F_out=F)
+    torch.cuda.synchronize()
+    ev[2].record()
+    for lam in lams[warmup:]:
+        eng.recommend(float(lam), 20, F_out=F)
+    ev[3].record()
+    # F GEMM alone
+    ev[4].record()
+    for _ in range(steps):
+        eng.resource(out=F)
+    ev[5].record()
+    torch.cuda.synchronize()
+    t_g = ev[0].elapsed_time(ev[1]) / steps * 1e-3
+    t_step = ev[2].elapsed_time(ev[3]) / steps * 1e-3
+    t_f = ev[4].elapsed_time(ev[5]) / steps * 1e-3
+    _, peak_burst, _, how = peaks()
+    flops = 2.0 * M * M * U
+    return {
+        "workload": f"hybrid spreading ml-1m shape ({U}x{M}, nnz(A)={sel.size}), top-20 full-rank filtered",
+        "g_build": {"ms": round(t_g * 1e3, 4), "tflops": round(flops / t_g / 1e12, 2), "kind": "u8 x4 digits, exact"},
+        "f_gemm": {"ms": round(t_f * 1e3, 4), "tflops": round(flops / t_f / 1e12, 2), "kind": "bf16 x3 planes"},
+        "lambda_step": {"ms": round(t_step * 1e3, 4), "users_per_s": round(U / t_step, 1),
+                        "what": "scale_w + F=A.W + filtered top-20, per lambda"},
+        "roofline": {"bound": "tensor", "achieved": round(flops / t_f / 1e12, 2), "peak": peak_burst,
+                     "unit": "TFLOP/s", "frac": round(flops / t_f / 1e12 / peak_burst, 4), "traffic": None,
+                     "note": f"useful flops 2*U*M^2 of F=A.W (one pass counted, 3 bf16 planes issued) / {how} bf16 peak"},
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--shape", default="ml-20m")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-spreading", action="store_true")
+    ap.add_argument("--mode", default="p2p", choices=["p2p", "nccl"], help="multi-GPU layer exchange")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the B200 path has no CPU fallback")
+    from lgcnhs_b200 import _lib, ops
+    from lgcnhs_b200.dist import RowPartitionedPropagation, init_dist
+
+    rank, world, local = init_dist()
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    barrier = (lambda: torch.distributed.barrier()) if world > 1 else None
+    d = load_shape(args.shape, rank, barrier)
+    adj_np, _ = train_adj(d)
+    n = d.n_users + d.n_items
+    nnz = int(adj_np.shape[1])
+    adj = torch.from_numpy(adj_np).to(dev)
+    torch.manual_seed(42)
+    users_w = torch.empty(d.n_users, DIM).normal_(std=0.1)
+    items_w = torch.empty(d.n_items, DIM).normal_(std=0.1)
+    x0_host = torch.cat([users_w, items_w]).pin_memory()
+    x0 = x0_host.to(dev)
+
+    if world == 1:
+        g = ops.NormGraph(adj, n)
+        E = torch.empty_like(x0)
+        tmp = (torch.empty_like(x0), torch.empty_like(x0))
+        step = lambda: g.propagate_mean(x0, K_LAYERS, out=E, tmp=tmp)  # noqa: E731
+        launches_per_step = K_LAYERS
+    else:
+        prop = RowPartitionedPropagation(adj, n, DIM, mode=args.mode)
+        step = lambda: prop.propagate_mean(x0, K_LAYERS)  # noqa: E731
+        launches_per_step = K_LAYERS
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+    _lib.reset_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with Clocks(local) as clk:
+        sync_all()
+        ev0.record()
+        for _ in range(args.steps):
+            step()
+        ev1.record()
+        sync_all()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    launches = _lib.launch_count()
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+    bytes_step = prop_bytes(nnz, n)
+    value = bytes_step / (ms * 1e-3) / 1e9
+
+    line = None
+    if rank == 0:
+        hbm, _, _, how = peaks()
+        line = {
+            "metric": "LightGCN prop GB/s", "value": round(value, 2), "unit": "GB/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 5), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"LightGCN K={K_LAYERS} D={DIM} fused propagation + layer mean, {args.shape} shape "
+                                   f"train graph (U={d.n_users}, M={d.n_items}, nnz={nnz}, N={n})",
+                       "l2": "inputs larger than L2 (CSR stream 8*nnz = %.0f MB per layer; X 42 MB is L2-resident by design)"
+                             % (8 * nnz / 1e6),
+                       "parallelism": "1 GPU" if world == 1 else f"row partition by nnz over {world} GPUs, {args.mode} exchange"},
+            "gpu_launches": int(launches),
+            "clocks": clk.summary(),
+        }
+        per_layer_ms = ms / K_LAYERS
+        compulsory = nnz * 8 + (n + 1) * 4 + 2 * n * 4 * DIM
+        line["roofline"] = {
+            "bound": "hbm", "achieved": round(value, 2), "peak": hbm, "unit": "GB/s", "frac": round(value / hbm, 4),
+            "traffic": None, "kernel": "spmm_layer_kernel<64,0>", "us_per_layer": round(per_layer_ms * 1e3, 2),
+            "compulsory_frac": round(compulsory / (per_layer_ms * 1e-3) / 1e9 / hbm, 4),
+            "note": f"algorithmic bytes = no-reuse model 264 B/nnz + 260 B/node per layer; peak = {how} HBM copy "
+                    "bandwidth; X is L2-resident so the no-reuse fraction may exceed 1 (SURVEY.md 8d)",
+        }
+
+    # ---- e2e through the reference-facing module call, host buffers, N GPUs ----
+    from model.LightGCN.model import LightGCN
+
+    if world == 1:
+        model = LightGCN(d.n_users, d.n_items, DIM, K_LAYERS).to(dev)
+        out_host = torch.empty((n, DIM), dtype=torch.float32).pin_memory()
+        with torch.no_grad():
+            def e2e_step():
+                model.users_emb.weight.copy_(x0_host[: d.n_users], non_blocking=True)
+                model.items_emb.weight.copy_(x0_host[d.n_users:], non_blocking=True)
+                uf, _, itf, _ = model.forward(adj)
+                out_host[: d.n_users].copy_(uf, non_blocking=True)
+                out_host[d.n_users:].copy_(itf, non_blocking=True)
+            for _ in range(3):
+                e2e_step()
+            sync_all()
+            ev0.record()
+            n_e2e = max(3, args.steps // 2)
+            for _ in range(n_e2e):
+                e2e_step()
+            ev1.record()
+            sync_all()
+        ms_e2e = ev0.elapsed_time(ev1) / n_e2e
+    else:
+        out_host = torch.empty((n, DIM), dtype=torch.float32).pin_memory()
+        def e2e_step():
+            x0.copy_(x0_host, non_blocking=True)
+            E = prop.propagate_mean(x0, K_LAYERS)
+            out_host.copy_(E, non_blocking=True)
+        for _ in range(3):
+            e2e_step()
+        sync_all()
+        ev0.record()
+        n_e2e = max(3, args.steps // 2)
+        for _ in range(n_e2e):
+            e2e_step()
+        ev1.record()
+        sync_all()
+        t = torch.tensor([ev0.elapsed_time(ev1) / n_e2e], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    if rank == 0:
+        line["e2e"] = {"value": round(bytes_step / (ms_e2e * 1e-3) / 1e9, 2), "unit": "GB/s",
+                       "ms_per_step": round(ms_e2e, 4), "h2d_bytes_per_step": int(x0_host.numel() * 4),
+                       "d2h_bytes_per_step": int(out_host.numel() * 4),
+                       "what": "LightGCN.forward(edge_index): pinned-host e^0 -> device, K fused layers, e^K-mean -> pinned host"}
+
+    # ---- the other two figures of the metric: W TFLOP/s and top-20 users/s (config 2), rank 0 ----
+    if rank == 0 and not args.no_spreading:
+        try:
+            line["spreading"] = spreading_leg(dev, steps=max(3, min(args.steps, 10)), warmup=3)
+        except Exception as e:  # keep the primary line even if the secondary leg fails
+            line["spreading"] = {"error": repr(e)[:300]}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        gbs, sec = cpu_prop_sample(adj_np, d.n_users, d.n_items, steps=1, warmup=1)
+        line["cpu_baseline"] = {"value": round(gbs, 3), "unit": "GB/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": "1 of 3 propagation layers over the full graph (PyG-equivalent oracle port: "
+                                          "gcn_norm + index_select + scatter_add); %.2f s per layer" % sec}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

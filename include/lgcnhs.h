@@ -190,6 +190,7 @@ int hs_pack_at(const int32_t* users, const int32_t* items, int64_t nnz, int64_t 
  * A: (M x K) K-major, B_p: `planes` matrices (N x K) K-major, plane stride in elements.
  * kind 0: bf16 operands, fp32 accumulate, w_p = 1                (planes in {1,2,3})
  * kind 1: uint8 operands, exact int32 accumulate, w_p = 256^p    (planes in {1,2,4})
+ * Tile: 128 rows x NB columns x all planes in one MMA (N = planes*NB: 128, 256, 240, 256).
  * Replaces np.dot(A.T / user_degrees, A) (model/SpreadMethod/model.py:25) and
  * np.dot(F0, W) (model/SpreadMethod/model.py:98).
  * lda/ldb in elements, multiples of 16 bytes; pointers 16-byte aligned (TMA).
@@ -199,6 +200,11 @@ int hs_gemm_planes(int32_t kind, const void* A, int64_t lda, const void* B, int6
                    int64_t plane_stride, int32_t planes, int64_t M, int64_t N, int64_t K,
                    float* C, int64_t ldc, const float* rs, const float* cs, double scale,
                    lgc_stream_t stream);
+/* tcgen05 kind::f16 accumulates with truncation (measured: tools/probe_umma_numerics.py), so
+ * the bf16 kind drains its TMEM accumulator into round-to-nearest fp32 registers every
+ * chunk_kb K-blocks of 64 elements (default 8): error <= 4*chunk_kb*2^-23 per output,
+ * independent of K.  Tuning/diagnostic knob. */
+int hs_gemm_config(int32_t chunk_kb);
 /* Plain CUDA-core fp32-accumulate version of the same contract, used by the GPU tests as
  * an on-device cross-check of the tcgen05 path (never by the product path). */
 int hs_gemm_planes_simt(int32_t kind, const void* A, int64_t lda, const void* B,
@@ -227,9 +233,10 @@ int hs_hadamard(float* F, const float* Gscore, int64_t rows, int64_t cols, int64
  * Multi-GPU support for the fused SpMM + all-gather (rows written straight into every
  * peer's replica over NVLink): CUDA IPC handle export / import for a device buffer.
  * ---------------------------------------------------------------------------------- */
-int lgc_ipc_get_handle(void* dptr, uint8_t* handle64_host);
-int lgc_ipc_open_handle(const uint8_t* handle64_host, void** dptr_host);
-int lgc_ipc_close_handle(void* dptr);
+/* blob = 64-byte cudaIpcMemHandle_t of the containing allocation + 8-byte offset of dptr in it */
+int lgc_ipc_get_handle(void* dptr, uint8_t* handle72_host);
+int lgc_ipc_open_handle(const uint8_t* handle72_host, void** dptr_host);
+int lgc_ipc_close_handle(void* base_dptr);
 /* Same as lgc_spmm_layer for rows [row_begin,row_end) but every finished row is stored
  * into n_peers output replicas (peer_Y_host[p] = device pointer valid in this process). */
 int lgc_spmm_layer_bcast(const int32_t* rowptr, const int32_t* colidx, const float* val,

@@ -11,6 +11,14 @@
 //          q_u = round(2^s / k_u); all products and sums are exact integers, the digit sums
 //          are recombined in float64 in the epilogue and rounded once to fp32.
 //
+// Accumulation numerics (measured on B200, tools/probe_umma_numerics.py): tcgen05 kind::f16
+// adds the 16 products of one MMA and the fp32 accumulator with TRUNCATION (round toward
+// zero, ~2 guard bits), so a long K loop is biased low by up to ~1 ulp per MMA step
+// (1.5e-5 at K=4100 on heavy-tailed data).  The bf16 kind therefore drains the TMEM
+// accumulator every `chunk_kb` K-blocks and carries the running sum in fp32 registers with
+// round-to-nearest adds: the truncation error is then relative to a chunk's partial sum and
+// bounded by (4*chunk_kb) * 2^-23, independent of K.  kind::i8 accumulates exactly in int32.
+//
 // Kernel shape (one persistent CTA per SM, 192 threads, warp-specialised):
 //   warp 0      TMA producer  : A tile 128 x 128B and `planes` B tiles NB x 128B per stage
 //                               (SWIZZLE_128B, K-major), 4-stage mbarrier ring
@@ -143,9 +151,10 @@ struct GemmParams {
   const float* cs;
   double scale;
   int k_elems_per_kb;  // 64 (bf16) or 128 (u8)
+  int chunk_kb;        // K-blocks accumulated in TMEM before a drain (>= num_kb: single chunk)
 };
 
-template <int KIND>
+template <int KIND, int PLANES>
 __global__ void __launch_bounds__(kThreads, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                  const GemmParams p) {
@@ -161,8 +170,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NB = PLANES == 3 ? 80 : PLANES == 4 ? 64 : 128;  // output columns per tile
   const int num_tiles = p.tiles_m * p.tiles_n;
-  const int n_mma = p.planes * p.NB;  // MMA N
+  constexpr int n_mma = PLANES * NB;  // MMA N
+  const int n_chunks = (p.num_kb + p.chunk_kb - 1) / p.chunk_kb;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -195,9 +206,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
           mbar_expect_tx(&full[stage], stage_tx);
           const int k0 = kb * p.k_elems_per_kb;
           tma_load_2d(&tmapA, &full[stage], smemA + stage * kAStage, k0, m_blk * kBlockM);
-          for (int pl = 0; pl < p.planes; ++pl)
-            tma_load_3d(&tmapB, &full[stage], smemB + stage * kBStage + pl * p.NB * kKBytes, k0,
-                        n_blk * p.NB, pl);
+#pragma unroll
+          for (int pl = 0; pl < PLANES; ++pl)
+            tma_load_3d(&tmapB, &full[stage], smemB + stage * kBStage + pl * NB * kKBytes, k0, n_blk * NB, pl);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -211,89 +222,100 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
     idesc |= ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
     int stage = 0;
     uint32_t phase = 0;
-    int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tempty[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * kAccStride;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        mbar_wait(&full[stage], phase);
+    int it = 0;  // accumulator-buffer use counter (one per chunk)
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int ch = 0; ch < n_chunks; ++ch, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
-        if (lane == 0) {
-          const uint64_t adesc = make_smem_desc(smem_u32(smemA + stage * kAStage));
-          const uint64_t bdesc = make_smem_desc(smem_u32(smemB + stage * kBStage));
+        const uint32_t d_tmem = tmem_base + acc * kAccStride;
+        const int kb0 = ch * p.chunk_kb;
+        const int kb1 = min(kb0 + p.chunk_kb, p.num_kb);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint64_t adesc = make_smem_desc(smem_u32(smemA + stage * kAStage));
+            const uint64_t bdesc = make_smem_desc(smem_u32(smemB + stage * kBStage));
 #pragma unroll
-          for (int k = 0; k < kKBytes / 32; ++k)  // 32 bytes of K per MMA: +2 in >>4 units
-            mma_ss<KIND>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          tc_commit(&empty[stage]);  // frees the smem stage when these MMAs retire
-          if (kb == p.num_kb - 1) tc_commit(&tfull[acc]);
+            for (int k = 0; k < kKBytes / 32; ++k)  // 32 bytes of K per MMA: +2 in >>4 units
+              mma_ss<KIND>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
+            tc_commit(&empty[stage]);  // frees the smem stage when these MMAs retire
+            if (kb == kb1 - 1) tc_commit(&tfull[acc]);
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else {
     // ------------------------------ epilogue (warps 2..5) ------------------------------
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m_blk = t % p.tiles_m, n_blk = t / p.tiles_m;
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
       const int64_t row = (int64_t)m_blk * kBlockM + q * 32 + lane;
       const bool row_ok = row < p.M;
       const float rscale = (row_ok && p.rs) ? __ldg(p.rs + row) : 1.0f;
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride;
       float* crow = p.C + (row_ok ? row : 0) * p.ldc;
-      for (int c0 = 0; c0 < p.NB; c0 += 16) {
-        uint32_t r[3][16];
-        float out[16];
-        // digits / split planes are at column offsets pl*NB inside the accumulator
-        tmem_ld16(t_row + c0, r[0]);
-        if (p.planes > 1) tmem_ld16(t_row + p.NB + c0, r[1]);
-        if (p.planes > 2) tmem_ld16(t_row + 2 * p.NB + c0, r[2]);
-        uint32_t r3[16];
-        if (KIND == 1 && p.planes > 3) tmem_ld16(t_row + 3 * p.NB + c0, r3);
-        tmem_ld_wait();
-        const int64_t col0 = (int64_t)n_blk * p.NB + c0;
+      float run[NB];  // running fp32 (round-to-nearest) sum over chunks, bf16 kind only
+      for (int ch = 0; ch < n_chunks; ++ch, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride;
+        const bool first = ch == 0, last = ch == n_chunks - 1;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float v;
-          if (KIND == 0) {
-            float a = __uint_as_float(r[0][j]);
-            if (p.planes == 2) a = __uint_as_float(r[1][j]) + a;
-            if (p.planes == 3) a = (__uint_as_float(r[2][j]) + __uint_as_float(r[1][j])) + a;
-            v = a * (float)p.scale;
-          } else {
-            long long tot = (long long)(int)r[0][j];
-            if (p.planes > 1) tot += (long long)(int)r[1][j] << 8;
-            if (p.planes > 2) tot += (long long)(int)r[2][j] << 16;
-            if (p.planes > 3) tot += (long long)(int)r3[j] << 24;
-            v = (float)((double)tot * p.scale);
+        for (int c0 = 0; c0 < NB; c0 += 16) {
+          uint32_t r[PLANES][16];
+#pragma unroll
+          for (int pl = 0; pl < PLANES; ++pl) tmem_ld16(t_row + pl * NB + c0, r[pl]);
+          tmem_ld_wait();
+          float out[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (KIND == 0) {
+              // planes hold hi / mid / lo: add the small ones first
+              float a = __uint_as_float(r[PLANES - 1][j]);
+#pragma unroll
+              for (int pl = PLANES - 2; pl >= 0; --pl) a += __uint_as_float(r[pl][j]);
+              if (!first) a += run[c0 + j];
+              run[c0 + j] = a;
+              out[j] = a * (float)p.scale;
+            } else {
+              long long tot = 0;  // exact: digits recombined in 64-bit integers, one rounding
+#pragma unroll
+              for (int pl = PLANES - 1; pl >= 0; --pl) tot = (tot << 8) + (long long)(int)r[pl][j];
+              out[j] = (float)((double)tot * p.scale);
+            }
           }
-          const int64_t col = col0 + j;
-          const float cscale = (p.cs && col < p.N) ? __ldg(p.cs + col) : 1.0f;
-          out[j] = v * rscale * cscale;
-        }
-        if (row_ok) {
-          if (col0 + 16 <= p.N && (p.ldc & 3) == 0 && ((uintptr_t)p.C & 15) == 0) {
+          if (last) {
+            const int64_t col0 = (int64_t)n_blk * NB + c0;
 #pragma unroll
-            for (int j = 0; j < 16; j += 4)
-              *reinterpret_cast<float4*>(crow + col0 + j) = make_float4(out[j], out[j + 1], out[j + 2], out[j + 3]);
-          } else {
+            for (int j = 0; j < 16; ++j) {
+              const int64_t col = col0 + j;
+              const float cscale = (p.cs && col < p.N) ? __ldg(p.cs + col) : 1.0f;
+              out[j] = out[j] * rscale * cscale;
+            }
+            if (row_ok) {
+              if (col0 + 16 <= p.N && (p.ldc & 3) == 0 && ((uintptr_t)p.C & 15) == 0) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (col0 + j < p.N) crow[col0 + j] = out[j];
+                for (int j = 0; j < 16; j += 4)
+                  *reinterpret_cast<float4*>(crow + col0 + j) = make_float4(out[j], out[j + 1], out[j + 2], out[j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (col0 + j < p.N) crow[col0 + j] = out[j];
+              }
+            }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
     }
   }
 
@@ -305,6 +327,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
                  : "memory");
   }
 }
+
+static int g_chunk_kb = 8;  // K-blocks (of 64 bf16) per TMEM accumulation chunk, see header comment
 
 // ---- host side: tensor maps through the driver entry point (no -lcuda link dependency) ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -386,7 +410,7 @@ extern "C" int hs_gemm_planes(int32_t kind, const void* A, int64_t lda, const vo
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) LGC_FAIL(LGC_ERR_CUDA, "gemm: cuTensorMapEncodeTiled entry point not available");
 
-  const int NB = planes == 1 ? 256 : planes == 2 ? 128 : planes == 3 ? 80 : 64;
+  const int NB = planes == 3 ? 80 : planes == 4 ? 64 : 128;
   const int k_elems = kKBytes / esize;
   const CUtensorMapDataType dt = kind == 0 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
 
@@ -420,25 +444,30 @@ extern "C" int hs_gemm_planes(int32_t kind, const void* A, int64_t lda, const vo
   p.tiles_n = (int)ceil_div(N, NB);
   p.C = C; p.ldc = ldc; p.rs = rs; p.cs = cs; p.scale = scale;
   p.k_elems_per_kb = k_elems;
+  p.chunk_kb = kind == 0 ? g_chunk_kb : p.num_kb;  // int32 accumulation is exact: one chunk
   const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (kind == 0) {
-    static bool attr0 = false;
-    if (!attr0) {
-      LGC_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-      attr0 = true;
-    }
-    umma_gemm_kernel<0><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, p);
-  } else {
-    static bool attr1 = false;
-    if (!attr1) {
-      LGC_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-      attr1 = true;
-    }
-    umma_gemm_kernel<1><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, p);
+#define LGC_GEMM_CASE(KD, PL)                                                                             \
+  if (kind == KD && planes == PL) {                                                                       \
+    static bool attr = false;                                                                             \
+    if (!attr) {                                                                                          \
+      LGC_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<KD, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    (int)kSmemBytes));                                                    \
+      attr = true;                                                                                        \
+    }                                                                                                     \
+    umma_gemm_kernel<KD, PL><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, p);                        \
   }
+  LGC_GEMM_CASE(0, 1) LGC_GEMM_CASE(0, 2) LGC_GEMM_CASE(0, 3)
+  LGC_GEMM_CASE(1, 1) LGC_GEMM_CASE(1, 2) LGC_GEMM_CASE(1, 4)
+#undef LGC_GEMM_CASE
   LGC_LAUNCH_CHECK("umma_gemm_kernel");
+  return LGC_OK;
+}
+
+extern "C" int hs_gemm_config(int32_t chunk_kb) {
+  LGC_REQUIRE(chunk_kb >= 1, "gemm config: chunk_kb must be >= 1");
+  g_chunk_kb = chunk_kb;
   return LGC_OK;
 }
 

@@ -43,6 +43,7 @@ _SIGS = {
     "hs_gemm_planes": (C.c_int, [_i32, _p, _i64, _p, _i64, _i64, _i32, _i64, _i64, _i64, _p, _i64, _p, _p, _f64, _p]),
     "hs_gemm_planes_simt": (C.c_int, [_i32, _p, _i64, _p, _i64, _i64, _i32, _i64, _i64, _i64, _p, _i64, _p, _p,
                                       _f64, _p]),
+    "hs_gemm_config": (C.c_int, [_i32]),
     "hs_scale_w": (C.c_int, [_p, _i64, _i64, _p, _f64, _p, _i64, _p, _i64, _i64, _i32, _p]),
     "hs_hadamard": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _p]),
     "lgc_ipc_get_handle": (C.c_int, [_p, _p]),
