@@ -1,0 +1,35 @@
+"""Short, deterministic launch sequence for ncu (never a bench value): a few propagation steps
+on the ml-20m train graph and a few spreading lambda-steps on the ml-1m shape."""
+import argparse, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402  (sets sys.path for the package)
+import numpy as np, torch  # noqa: E402
+from lgcnhs_b200 import ops  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--what", default="prop", choices=["prop", "spread", "both"])
+ap.add_argument("--shape", default="ml-20m")
+ap.add_argument("--steps", type=int, default=2)
+a = ap.parse_args()
+dev = torch.device("cuda:0")
+if a.what in ("prop", "both"):
+    d = bench.load_shape(a.shape)
+    adj_np, _ = bench.train_adj(d)
+    n = d.n_users + d.n_items
+    g = ops.NormGraph(torch.from_numpy(adj_np).to(dev), n)
+    torch.manual_seed(42)
+    x0 = (torch.randn(n, 64) * 0.1).to(dev)
+    for _ in range(a.steps + 1):
+        E = g.propagate_mean(x0, 3)
+    torch.cuda.synchronize()
+    print("prop ok", float(E.abs().sum()))
+if a.what in ("spread", "both"):
+    d = bench.load_shape("ml-1m")
+    tr, va, _ = d.split()
+    sel = np.concatenate([tr, va])
+    eng = ops.SpreadingEngine(d.n_users, d.n_items, torch.from_numpy(d.users[sel]).to(dev), torch.from_numpy(d.items[sel]).to(dev))
+    for lam in np.linspace(0.2, 0.8, a.steps + 1):
+        idx, val = eng.recommend(float(lam), 20)
+    torch.cuda.synchronize()
+    print("spread ok", int(idx.sum()))
