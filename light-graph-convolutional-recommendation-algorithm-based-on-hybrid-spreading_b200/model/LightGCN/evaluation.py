@@ -1,0 +1,47 @@
+"""Drop-in for /root/reference/model/LightGCN/evaluation.py (getValRecommendations, calValLoss)."""
+import torch
+
+from lgcnhs_b200 import ops
+from lgcnhs_b200.sampling import structured_negative_sampling
+from model.LightGCN.model import LightGCN
+from utils.graph import convertAdjMatrixToEdgeIndex
+
+
+def _topk_layer0(model, user_num: int, item_num: int, exclude_edge_indices, k: int) -> torch.Tensor:
+    """score = e_u^0 . e_i^0^T (LAYER-0 weights, reference evaluation.py:31-34 / recommend.py:83-86),
+    seen pairs set to -1024, top-k — computed block-wise so the (U, M) matrix never exists."""
+    xu = model.users_emb.weight.detach().contiguous()
+    xi = model.items_emb.weight.detach().contiguous()
+    dev = xu.device
+    uu = torch.cat([e[0] for e in exclude_edge_indices]).to(dev)
+    ii = torch.cat([e[1] for e in exclude_edge_indices]).to(dev)
+    seen = ops.seen_csr(uu, ii, user_num, item_num)
+    blk = max(64, min(user_num, (1 << 28) // max(item_num, 1)))     # <= 1 GiB of scores per block
+    out = torch.empty((user_num, k), dtype=torch.int64, device=dev)
+    buf = torch.empty((min(blk, user_num), (item_num + 3) // 4 * 4), dtype=torch.float32, device=dev)
+    for u0 in range(0, user_num, blk):
+        u1 = min(u0 + blk, user_num)
+        s = ops.score_block(xu, xi, u0, u1, seen, fill=-float(1 << 10), out=buf[: u1 - u0, :item_num])
+        idx, _ = ops.topk_rows(s, k, want_values=False)
+        out[u0:u1] = idx
+    return out
+
+
+def getValRecommendations(model: LightGCN, user_num: int, item_num: int,
+                          train_edge_index: torch.Tensor, val_edge_index: torch.Tensor, k: int) -> torch.Tensor:
+    """(U, k) recommendations for validation: only TRAIN pairs are masked (reference evaluation.py:36-52)."""
+    train_ei = convertAdjMatrixToEdgeIndex(user_num, item_num, train_edge_index)
+    return _topk_layer0(model, user_num, item_num, [train_ei], k)
+
+
+def calValLoss(model: LightGCN, user_num: int, item_num: int, val_edge_index: torch.Tensor,
+               lambda_val: float) -> float:
+    """BPR loss over ALL validation edges, propagating over the VAL graph (reference evaluation.py:56-86)."""
+    users_f, users_0, items_f, items_0 = model.forward(val_edge_index)
+    r_mat = convertAdjMatrixToEdgeIndex(user_num, item_num, val_edge_index)
+    u, p, n = structured_negative_sampling(r_mat, contains_neg_self_loops=False)
+    n = n.clamp_(max=item_num - 1)   # the reference indexes items with neg in [0, max(U,M)): out of range when U > M
+    E = torch.cat([users_f, items_f]).detach().contiguous()
+    X0 = torch.cat([users_0, items_0]).detach().contiguous()
+    loss = ops.bpr_fwd_bwd(E, X0, user_num, item_num, u.contiguous(), p.contiguous(), n.contiguous(), lambda_val)
+    return round(loss[0].item(), 5)
