@@ -90,6 +90,9 @@ int lgc_spmm_layer(const int32_t* rowptr, const int32_t* colidx, const float* va
                    const float* X, const float* X0, float alpha, float beta, float* Y,
                    float* partial, int32_t* counters, lgc_stream_t stream);
 
+/* Tuning knob: independent 128-bit gathers in flight per lane for dim 64 (2, 4 or 8). */
+int lgc_spmm_config(int32_t unroll);
+
 /* K-layer forward with the uniform layer mean in Horner form
  *   S_0 = X0,  S_{l+1} = A_hat S_l + X0,  E = S_K / (K+1)
  * == mean(stack([X0, A X0, ..., A^K X0])) of model/LightGCN/model.py:56-69.

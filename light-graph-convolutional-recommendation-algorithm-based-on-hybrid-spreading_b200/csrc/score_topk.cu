@@ -81,10 +81,18 @@ __global__ void seen_fill_kernel(const int32_t* __restrict__ seen_ptr, const int
 }
 
 // ------------------------------------------------------------------------------------------
-// row-wise masked top-k (radix select on a 64-bit composite key = (ordered value, index))
+// row-wise masked top-k: radix select on the 64-bit composite key (ordered fp32 value, index)
 // ------------------------------------------------------------------------------------------
+// One CTA per row.  The row is read from global memory ONCE (when it has <= 256*RCACHE columns)
+// into per-thread registers as order-preserving 32-bit keys with the exclusion applied.  MSB-first
+// 11-bit digits of the composite key are histogrammed until the undecided bucket plus everything
+// above it fits a 256-entry candidate buffer, which is then sorted (bitonic) — typically two
+// digit passes for continuous scores, six only when the whole row ties.  Exact and deterministic;
+// equal values rank the LARGER index first (np.argsort(row)[::-1] / CPU torch.topk order).
 constexpr int kTopkThreads = 256;
 constexpr int kTopkMaxK = 128;
+constexpr int kCand = 256;
+constexpr int kBins = 2048;
 
 __device__ __forceinline__ uint32_t float_key(float x) {
   const uint32_t b = __float_as_uint(x);
@@ -95,14 +103,17 @@ __device__ __forceinline__ float key_float(uint32_t k) {
 }
 
 struct TopkSmem {
-  unsigned int hist[256];
-  unsigned long long sel[kTopkMaxK];
-  unsigned long long prefix;
-  int remaining;
-  int n_sel;
-  int digit;
+  unsigned int hist[kBins];
+  unsigned long long cand[kCand];
+  unsigned int warp_tot[kTopkThreads / 32];
+  unsigned long long prefix;  // decided high bits of the k-th largest key (low bits zero)
+  int k_rem;                  // how many are still to be taken from the undecided bucket
+  int n_above;                // elements strictly above the undecided bucket (all selected)
+  int n_eq;                   // elements in the undecided bucket
+  int n_cand;
 };
 
+template <int RCACHE>
 __global__ void __launch_bounds__(kTopkThreads)
 topk_rows_kernel(const float* __restrict__ S, int64_t n_cols, int64_t lds, const int32_t* __restrict__ excl_ptr,
                  const int32_t* __restrict__ excl_idx, int64_t row_offset, int k, int64_t* __restrict__ out_idx,
@@ -112,12 +123,12 @@ topk_rows_kernel(const float* __restrict__ S, int64_t n_cols, int64_t lds, const
   unsigned int* bitmap = s_dyn;  // n_cols bits: 1 = excluded
   const int64_t r = blockIdx.x;
   const float* row = S + r * lds;
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = (int)n_cols;
   const int words = (n + 31) / 32;
 
   for (int w = tid; w < words; w += kTopkThreads) bitmap[w] = 0u;
-  if (tid == 0) { sm.prefix = 0ull; sm.remaining = k; sm.n_sel = 0; }
+  if (tid == 0) { sm.prefix = 0ull; sm.k_rem = k; sm.n_above = 0; sm.n_eq = n; sm.n_cand = 0; }
   __syncthreads();
   if (excl_ptr) {
     const int s = excl_ptr[row_offset + r], e = excl_ptr[row_offset + r + 1];
@@ -128,81 +139,130 @@ topk_rows_kernel(const float* __restrict__ S, int64_t n_cols, int64_t lds, const
   }
   __syncthreads();
 
-  // composite key of column c; excluded columns get key 0 (below every real value)
-  auto comp_key = [&](int c) -> unsigned long long {
+  auto load_key = [&](int c) -> uint32_t {  // excluded columns get key 0 (below every real value)
     const bool ex = (bitmap[c >> 5] >> (c & 31)) & 1u;
-    const uint32_t vk = ex ? 0u : float_key(__ldg(row + c));
-    return ((unsigned long long)vk << 32) | (unsigned int)c;
+    return ex ? 0u : float_key(__ldg(row + c));
+  };
+  uint32_t kreg[RCACHE > 0 ? RCACHE : 1];
+  if (RCACHE > 0) {
+#pragma unroll
+    for (int i = 0; i < RCACHE; ++i) {
+      const int c = tid + i * kTopkThreads;
+      kreg[i] = c < n ? load_key(c) : 0u;
+    }
+  }
+  // visit every column of the row: f(column, composite key)
+  auto for_each = [&](auto&& f) {
+    if (RCACHE > 0) {
+#pragma unroll
+      for (int i = 0; i < RCACHE; ++i) {
+        const int c = tid + i * kTopkThreads;
+        f(c, c < n, ((unsigned long long)kreg[i] << 32) | (unsigned int)c);
+      }
+    } else {
+      for (int c0 = 0; c0 < n; c0 += kTopkThreads) {
+        const int c = c0 + tid;
+        f(c, c < n, c < n ? (((unsigned long long)load_key(c) << 32) | (unsigned int)c) : 0ull);
+      }
+    }
   };
 
-  // MSB-first radix select over the 8 bytes of the composite key.  After the 4 value bytes
-  // the low (index) bytes only matter when equal values straddle the k-th position.
-  const int idx_bytes = n <= (1 << 8) ? 1 : n <= (1 << 16) ? 2 : n <= (1 << 24) ? 3 : 4;
-  for (int byte = 7; byte >= 0; --byte) {
-    if (byte < 4 && byte >= idx_bytes) continue;  // index bytes that are always zero
-    for (int b = tid; b < 256; b += kTopkThreads) sm.hist[b] = 0u;
+  // digit schedule over the 64-bit composite key: 11 + 11 + 10 value bits, then the index bits
+  int idx_bits = 1;
+  while ((1 << idx_bits) < n) ++idx_bits;
+  int shift = 64;
+  for (int pass = 0; pass < 8; ++pass) {
+    if (sm.n_above + sm.n_eq <= kCand) break;  // block-uniform (read after a barrier)
+    int width;
+    if (shift > 32) width = shift == 64 ? 11 : shift == 53 ? 11 : 10;
+    else {
+      const int top = shift == 32 ? idx_bits : shift;  // index bits above idx_bits are always zero
+      if (shift == 32) shift = idx_bits;
+      width = top < 11 ? top : 11;
+    }
+    if (width <= 0) break;
+    shift -= width;
+    for (int b = tid; b < kBins; b += kTopkThreads) sm.hist[b] = 0u;
     __syncthreads();
     const unsigned long long prefix = sm.prefix;
-    const int shift = byte * 8;
-    const unsigned long long hi_mask = byte == 7 ? 0ull : (~0ull << (shift + 8));
-    for (int c0 = 0; c0 < n; c0 += kTopkThreads) {
-      const int c = c0 + tid;
-      bool act = c < n;
-      unsigned int dg = 0;
-      if (act) {
-        const unsigned long long key = comp_key(c);
-        act = (key & hi_mask) == prefix;
-        dg = (unsigned int)(key >> shift) & 255u;
-      }
+    const unsigned long long hi_mask = (shift + width) >= 64 ? 0ull : (~0ull << (shift + width));
+    const unsigned int dmask = (1u << width) - 1u;
+    for_each([&](int, bool valid, unsigned long long key) {
+      const bool act = valid && (key & hi_mask) == prefix;
+      const unsigned int dg = (unsigned int)(key >> shift) & dmask;
       const unsigned int amask = __ballot_sync(0xffffffffu, act);
       if (act) {
         const unsigned int peers = __match_any_sync(amask, dg);
         if (lane == __ffs(peers) - 1) atomicAdd(&sm.hist[dg], (unsigned int)__popc(peers));
       }
-    }
+    });
     __syncthreads();
-    if (tid == 0) {
-      int rem = sm.remaining, d = 255;
-      for (; d > 0; --d) {
-        const int cnt = (int)sm.hist[d];
-        if (cnt >= rem) break;
-        rem -= cnt;
+    // find the bucket holding the k_rem-th largest: descending scan over the bins
+    constexpr int PER = kBins / kTopkThreads;  // 8 bins per thread, thread 0 owns the TOP bins
+    unsigned int mine = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) mine += sm.hist[kBins - 1 - (tid * PER + i)];
+    unsigned int incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += t;
+    }
+    if (lane == 31) sm.warp_tot[warp] = incl;
+    __syncthreads();
+    unsigned int before = 0;
+    for (int w = 0; w < warp; ++w) before += sm.warp_tot[w];
+    const unsigned int excl_sum = before + incl - mine;  // elements in bins above this thread's bins
+    const unsigned int k_rem = (unsigned int)sm.k_rem;
+    __syncthreads();
+    if (excl_sum < k_rem && excl_sum + mine >= k_rem) {  // exactly one thread
+      unsigned int acc = excl_sum;
+      for (int i = 0; i < PER; ++i) {
+        const int bin = kBins - 1 - (tid * PER + i);
+        const unsigned int cnt = sm.hist[bin];
+        if (acc + cnt >= k_rem) {
+          sm.prefix = prefix | ((unsigned long long)bin << shift);
+          sm.k_rem = (int)(k_rem - acc);
+          sm.n_above += (int)acc;
+          sm.n_eq = (int)cnt;
+          break;
+        }
+        acc += cnt;
       }
-      sm.remaining = rem;  // how many to take from bucket d (and below it in later bytes)
-      sm.prefix = prefix | ((unsigned long long)d << shift);
     }
     __syncthreads();
   }
-  // sm.prefix is now the exact composite key of the k-th largest element
-  const unsigned long long thr = sm.prefix;
-  for (int c0 = 0; c0 < n; c0 += kTopkThreads) {
-    const int c = c0 + tid;
-    if (c < n) {
-      const unsigned long long key = comp_key(c);
-      if (key >= thr) {
-        const int pos = atomicAdd(&sm.n_sel, 1);
-        if (pos < kTopkMaxK) sm.sel[pos] = key;
+  // everything >= prefix (at the decided precision) is a candidate: n_above + n_eq <= kCand of them,
+  // or exactly k when all digits were consumed
+  {
+    const unsigned long long thr = sm.prefix;
+    for_each([&](int, bool valid, unsigned long long key) {
+      if (valid && key >= thr) {
+        const int pos = atomicAdd(&sm.n_cand, 1);
+        if (pos < kCand) sm.cand[pos] = key;
       }
-    }
+    });
   }
   __syncthreads();
-  for (int i = sm.n_sel + tid; i < kTopkMaxK; i += kTopkThreads) sm.sel[i] = 0ull;
+  const int n_cand = min(sm.n_cand, kCand);
+  int sort_n = 32;
+  while (sort_n < n_cand) sort_n <<= 1;
+  for (int i = n_cand + tid; i < sort_n; i += kTopkThreads) sm.cand[i] = 0ull;
   __syncthreads();
-  // bitonic sort of 128 keys, descending
-  for (int size = 2; size <= kTopkMaxK; size <<= 1) {
+  for (int size = 2; size <= sort_n; size <<= 1) {  // bitonic sort, descending
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      if (tid < kTopkMaxK / 2) {
+      if (tid < sort_n / 2) {
         const int lo = 2 * tid - (tid & (stride - 1));
         const int hi = lo + stride;
         const bool desc = ((lo & size) == 0);
-        const unsigned long long a = sm.sel[lo], b = sm.sel[hi];
-        if ((a < b) == desc) { sm.sel[lo] = b; sm.sel[hi] = a; }
+        const unsigned long long a = sm.cand[lo], b = sm.cand[hi];
+        if ((a < b) == desc) { sm.cand[lo] = b; sm.cand[hi] = a; }
       }
       __syncthreads();
     }
   }
   if (tid < k) {
-    const unsigned long long key = sm.sel[tid];
+    const unsigned long long key = sm.cand[tid];
     out_idx[r * k + tid] = (int64_t)(unsigned int)(key & 0xffffffffull);
     if (out_val) out_val[r * k + tid] = key_float((uint32_t)(key >> 32));
   }
@@ -245,13 +305,22 @@ extern "C" int lgc_topk_rows(const float* S, int64_t n_rows, int64_t n_cols, int
   LGC_REQUIRE((excl_ptr == nullptr) == (excl_idx == nullptr), "topk: excl_ptr / excl_idx mismatch");
   const size_t dyn = (size_t)((n_cols + 31) / 32) * sizeof(unsigned int);
   LGC_REQUIRE(dyn <= 160 * 1024, "topk: more than 1.3M columns per row is not supported");
-  static size_t dyn_set = 48 * 1024;
-  if (dyn > dyn_set) {
-    LGC_CUDA(cudaFuncSetAttribute(topk_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    dyn_set = dyn;
-  }
-  topk_rows_kernel<<<(unsigned)n_rows, kTopkThreads, dyn, (cudaStream_t)stream>>>(
-      S, n_cols, lds, excl_ptr, excl_idx, row_offset, k, out_idx, out_val);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LGC_TOPK_LAUNCH(RC)                                                                                  \
+  do {                                                                                                       \
+    static size_t dyn_set = 32 * 1024;                                                                       \
+    if (dyn > dyn_set) {                                                                                     \
+      LGC_CUDA(cudaFuncSetAttribute(topk_rows_kernel<RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
+      dyn_set = dyn;                                                                                         \
+    }                                                                                                        \
+    topk_rows_kernel<RC><<<(unsigned)n_rows, kTopkThreads, dyn, st>>>(S, n_cols, lds, excl_ptr, excl_idx,    \
+                                                                      row_offset, k, out_idx, out_val);      \
+  } while (0)
+  if (n_cols <= 8 * kTopkThreads) LGC_TOPK_LAUNCH(8);
+  else if (n_cols <= 16 * kTopkThreads) LGC_TOPK_LAUNCH(16);
+  else if (n_cols <= 32 * kTopkThreads) LGC_TOPK_LAUNCH(32);
+  else LGC_TOPK_LAUNCH(0);
+#undef LGC_TOPK_LAUNCH
   LGC_LAUNCH_CHECK("topk_rows_kernel");
   return LGC_OK;
 }

@@ -25,8 +25,9 @@ namespace lgc {
 
 constexpr int kWarpsPerBlock = 8;
 constexpr int kThreads = kWarpsPerBlock * 32;
-constexpr int kUnroll = 4;
 constexpr int kMaxPeers = 8;
+
+static int g_spmm_unroll = 0;  // gathers in flight per lane for DIM=64; 0 = choose by grid size (lgc_spmm_config)
 
 struct PeerPtrs {
   float* y[kMaxPeers];
@@ -38,7 +39,10 @@ __device__ __forceinline__ float4 ld_row4(const float* p) {
 
 // Sum of val[e] * X[colidx[e], :] over e in [start, end) for one warp.  On return every
 // lane li of every sub-group holds the full sum for columns [4*li, 4*li+4).
-template <int DIM>
+// UN independent 128-bit gathers are in flight per lane, and the (colidx, val) metadata of the
+// next 32 non-zeros is requested before the gathers of the current 32 are issued, so the
+// dependent metadata -> gather chain is overlapped.
+template <int DIM, int UN>
 __device__ __forceinline__ float4 warp_gather_sum(const int32_t* __restrict__ colidx,
                                                   const float* __restrict__ val,
                                                   const float* __restrict__ X, int start, int end,
@@ -47,20 +51,25 @@ __device__ __forceinline__ float4 warp_gather_sum(const int32_t* __restrict__ co
   constexpr int SUB = 32 / LPR;  // rows in flight per warp-wide load
   const int sub = lane / LPR, li = lane % LPR;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int c = 0;
+  float v = 0.f;
+  if (start + lane < end) {
+    c = __ldcs(colidx + start + lane);
+    v = __ldcs(val + start + lane);
+  }
   for (int base = start; base < end; base += 32) {
-    const int idx = base + lane;
-    int c = 0;
-    float v = 0.f;
-    if (idx < end) {
-      c = __ldcs(colidx + idx);
-      v = __ldcs(val + idx);
+    int c_next = 0;
+    float v_next = 0.f;
+    if (base + 32 + lane < end) {
+      c_next = __ldcs(colidx + base + 32 + lane);
+      v_next = __ldcs(val + base + 32 + lane);
     }
     const int n = min(32, end - base);
-    for (int j = 0; j < n; j += SUB * kUnroll) {
-      float4 x[kUnroll];
-      float w[kUnroll];
+    for (int j = 0; j < n; j += SUB * UN) {
+      float4 x[UN];
+      float w[UN];
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
+      for (int u = 0; u < UN; ++u) {
         const int jj = j + u * SUB + sub;
         const int cc = __shfl_sync(0xffffffffu, c, jj & 31);
         const float vv = __shfl_sync(0xffffffffu, v, jj & 31);
@@ -69,13 +78,15 @@ __device__ __forceinline__ float4 warp_gather_sum(const int32_t* __restrict__ co
         x[u] = ok ? ld_row4(X + (size_t)cc * DIM + li * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
+      for (int u = 0; u < UN; ++u) {
         acc.x = fmaf(w[u], x[u].x, acc.x);
         acc.y = fmaf(w[u], x[u].y, acc.y);
         acc.z = fmaf(w[u], x[u].z, acc.z);
         acc.w = fmaf(w[u], x[u].w, acc.w);
       }
     }
+    c = c_next;
+    v = v_next;
   }
 #pragma unroll
   for (int off = LPR; off < 32; off <<= 1) {
@@ -98,7 +109,7 @@ __device__ __forceinline__ void store_row4(float* Y, const PeerPtrs& peers, size
   }
 }
 
-template <int DIM, int NPEER>
+template <int DIM, int NPEER, int UN>
 __global__ void __launch_bounds__(kThreads)
 spmm_layer_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                   const float* __restrict__ val, const int32_t* __restrict__ chunk_row,
@@ -117,7 +128,7 @@ spmm_layer_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
     if (row >= row_end) return;
     const int start = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
     if (end - start > LGC_LONG_ROW) return;  // handled by the chunk CTAs
-    float4 acc = warp_gather_sum<DIM>(colidx, val, X, start, end, lane);
+    float4 acc = warp_gather_sum<DIM, UN>(colidx, val, X, start, end, lane);
     if (lane < LPR) {
       const size_t off = (size_t)row * DIM + lane * 4;
       if (beta != 0.f) {
@@ -143,7 +154,7 @@ spmm_layer_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
   const int cend = min(cstart + LGC_CHUNK, rend);
   constexpr int PER_WARP = LGC_CHUNK / kWarpsPerBlock;
   const int wstart = min(cstart + warp * PER_WARP, cend), wend = min(wstart + PER_WARP, cend);
-  float4 acc = warp_gather_sum<DIM>(colidx, val, X, wstart, wend, lane);
+  float4 acc = warp_gather_sum<DIM, UN>(colidx, val, X, wstart, wend, lane);
   if (lane < LPR) *reinterpret_cast<float4*>(&s_part[warp][lane * 4]) = acc;
   __syncthreads();
   const int nch = (rend - rstart + LGC_CHUNK - 1) / LGC_CHUNK;
@@ -197,14 +208,24 @@ static int launch_spmm(const int32_t* rowptr, const int32_t* colidx, const float
   const int64_t n_rows = row_end - row_begin;
   const int64_t grid = n_chunk_blocks + ceil_div(n_rows, kWarpsPerBlock);
   if (grid == 0) return LGC_OK;
-#define LGC_SPMM_LAUNCH(D)                                                                        \
-  spmm_layer_kernel<D, NPEER><<<(unsigned)grid, kThreads, 0, stream>>>(                           \
+#define LGC_SPMM_LAUNCH(D, UNR)                                                                   \
+  spmm_layer_kernel<D, NPEER, UNR><<<(unsigned)grid, kThreads, 0, stream>>>(                      \
       rowptr, colidx, val, chunk_row, chunk_start, row_chunk_base, chunk_begin, n_chunk_blocks,   \
       (int)row_begin, (int)row_end, X, X0, alpha, beta, Y, peers, partial, counters, NPEER)
   switch (dim) {
-    case 32: LGC_SPMM_LAUNCH(32); break;
-    case 64: LGC_SPMM_LAUNCH(64); break;
-    case 128: LGC_SPMM_LAUNCH(128); break;
+    case 32: LGC_SPMM_LAUNCH(32, 4); break;
+    case 64:
+      {
+        // measured on B200 (tools/spmm_tune.py): with more than one full wave of CTAs, occupancy
+        // (32 regs, 64 warps/SM) beats per-warp ILP; with a single wave the deeper unroll wins
+        int un = g_spmm_unroll;
+        if (un == 0) un = grid > (int64_t)num_sms() * 8 * 2 ? 2 : 4;
+        if (un == 8) LGC_SPMM_LAUNCH(64, 8);
+        else if (un == 2) LGC_SPMM_LAUNCH(64, 2);
+        else LGC_SPMM_LAUNCH(64, 4);
+      }
+      break;
+    case 128: LGC_SPMM_LAUNCH(128, 4); break;
     default: LGC_FAIL(LGC_ERR_UNSUPPORTED, "spmm: embedding dim %d not in {32,64,128}", dim);
   }
 #undef LGC_SPMM_LAUNCH
@@ -231,6 +252,12 @@ static int check_spmm_args(const int32_t* rowptr, const int32_t* colidx, const f
 }  // namespace lgc
 
 using namespace lgc;
+
+extern "C" int lgc_spmm_config(int32_t unroll) {
+  LGC_REQUIRE(unroll == 0 || unroll == 2 || unroll == 4 || unroll == 8, "spmm config: unroll must be 0 (auto), 2, 4 or 8");
+  g_spmm_unroll = unroll;
+  return LGC_OK;
+}
 
 extern "C" int lgc_spmm_layer(const int32_t* rowptr, const int32_t* colidx, const float* val,
                               const int32_t* chunk_row, const int32_t* chunk_start,
