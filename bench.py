@@ -37,6 +37,10 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 K_LAYERS, DIM = 3, 64
+# dram__bytes_read.sum + dram__bytes_write.sum per spmm_layer_kernel launch from the committed
+# `ncu --set full` capture (profiles/r1_ncu_spmm.txt, ml-20m train graph): ~compulsory traffic, the
+# gathers are served by L2
+NCU_SPMM_DRAM_BYTES = {"ml-20m": 462_000_000}
 
 
 def peaks():
@@ -52,38 +56,64 @@ def peaks():
 # clocks sampler (nvidia-smi during the timed region)
 # ------------------------------------------------------------------------------------------
 class Clocks:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clock / throttle-reason sampler: one streaming process (-lms 20) started before the
+    warm-up; summary() keeps the samples whose timestamp falls inside the timed region (all samples
+    taken under load if the region is shorter than the sampling period)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+        import tempfile
 
-    def _run(self):
-        while not self._stop.is_set():
+        self.path = tempfile.mktemp(prefix="lgc_clocks_", suffix=".csv")
+        self.f = open(self.path, "w")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        self.t0 = self.t1 = None
+
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
+
+    def stop(self):
+        if self.proc is not None:
+            time.sleep(0.05)
+            self.proc.terminate()
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
+                self.proc.wait(timeout=5)
             except Exception:
-                pass
-            self._stop.wait(0.2)
-
-    def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
-        return self
-
-    def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+                self.proc.kill()
+        self.f.close()
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        import datetime
+
+        rows = []
+        try:
+            for line in open(self.path):
+                c = [x.strip() for x in line.strip().split(",")]
+                if len(c) < 7:
+                    continue
+                try:
+                    ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    rows.append((ts, float(c[1]), float(c[2]), c[3:7]))
+                except ValueError:
+                    continue
+        except OSError:
+            pass
+        inside = [r for r in rows if self.t0 is not None and self.t0 - 0.02 <= r[0] <= self.t1 + 0.02]
+        use = inside if inside else rows[-5:]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower() == "active"})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        reasons = sorted({n for r in use for n, v in zip(names, r[3]) if v.lower() == "active"})
+        return {"sm_mhz": float(np.median([r[1] for r in use])) if use else None,
+                "sm_max_mhz": max((r[2] for r in use), default=None), "reasons": reasons,
+                "samples": len(inside), "samples_total": len(rows)}
 
 
 # ------------------------------------------------------------------------------------------
@@ -142,7 +172,7 @@ def run_reference(args):
         return
     d = load_shape(args.shape)
     adj, _ = train_adj(d)
-    steps, warmup = max(1, min(args.steps, 3)), 1
+    steps, warmup = max(1, min(args.steps, 40)), max(0, min(args.warmup, 3))   # ~1.5 s per step on 16 cores
     gbs, sec = cpu_prop_sample(adj, d.n_users, d.n_items, steps, warmup)
     cores = torch.get_num_threads()
     line = {
@@ -266,18 +296,21 @@ def main():
             torch.distributed.barrier()
             torch.cuda.synchronize()
 
+    clk = Clocks(local)
     for _ in range(args.warmup):
         step()
     sync_all()
     _lib.reset_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with Clocks(local) as clk:
-        sync_all()
-        ev0.record()
-        for _ in range(args.steps):
-            step()
-        ev1.record()
-        sync_all()
+    sync_all()
+    clk.begin()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    sync_all()
+    clk.end()
+    clk.stop()
     ms = ev0.elapsed_time(ev1) / args.steps
     launches = _lib.launch_count()
     if world > 1:
@@ -306,7 +339,8 @@ def main():
         compulsory = nnz * 8 + (n + 1) * 4 + 2 * n * 4 * DIM
         line["roofline"] = {
             "bound": "hbm", "achieved": round(value, 2), "peak": hbm, "unit": "GB/s", "frac": round(value / hbm, 4),
-            "traffic": None, "kernel": "spmm_layer_kernel<64,0>", "us_per_layer": round(per_layer_ms * 1e3, 2),
+            "traffic": NCU_SPMM_DRAM_BYTES.get(args.shape), "kernel": "spmm_layer_kernel<64,0,UN>",
+            "us_per_layer": round(per_layer_ms * 1e3, 2),
             "compulsory_frac": round(compulsory / (per_layer_ms * 1e-3) / 1e9 / hbm, 4),
             "note": f"algorithmic bytes = no-reuse model 264 B/nnz + 260 B/node per layer; peak = {how} HBM copy "
                     "bandwidth; X is L2-resident so the no-reuse fraction may exceed 1 (SURVEY.md 8d)",

@@ -156,15 +156,20 @@ int lgc_score_block(const float* Xu, const float* Xi, int64_t u0, int64_t u1,
  * (P8/S4) Row-wise masked top-k.  Replaces torch.topk(score, k)
  * (model/LightGCN/recommend.py:114) and the argsort + Python filter loop of
  * model/SpreadMethod/recommend.py:35-47 (== SpreadLightGCN/recommend.py:34-46).
- *   S: (n_rows, n_cols) fp32, ld = lds.  Row r corresponds to user row_offset + r of
- *   the exclusion CSR (excl_ptr/excl_idx, may be null).  Excluded entries can never be
- *   selected.  Result sorted by value descending, ties -> larger index first (what the
- *   CPU reference produces for np.argsort(row)[::-1]).
+ *   S: (n_rows, n_cols) fp32, ld = lds.  excl_mask (may be null) is a bit-packed matrix, bit
+ *   (row_offset + r) * mask_stride_bits + c set = column c can never be selected for row r —
+ *   the deduplicated interaction bitmap hs_degrees() produces, or lgc_mask_from_csr().
+ *   Result sorted by value descending, ties -> larger index first (what the CPU reference
+ *   produces for np.argsort(row)[::-1]).
  *   out_idx int64 (n_rows, k), out_val fp32 (n_rows, k) or null.  k <= 128, k <= n_cols.
  * ---------------------------------------------------------------------------------- */
 int lgc_topk_rows(const float* S, int64_t n_rows, int64_t n_cols, int64_t lds,
-                  const int32_t* excl_ptr, const int32_t* excl_idx, int64_t row_offset,
+                  const uint32_t* excl_mask, int64_t mask_stride_bits, int64_t row_offset,
                   int32_t k, int64_t* out_idx, float* out_val, lgc_stream_t stream);
+/* CSR (rowptr, column ids) -> bit-packed mask with the given row stride; mask zero-filled by
+ * the caller, (n_rows * stride_bits + 31) / 32 words. */
+int lgc_mask_from_csr(const int32_t* ptr, const int32_t* idx, int64_t n_rows, int64_t n_cols,
+                      int64_t stride_bits, uint32_t* mask, lgc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * (S0/S1) Hybrid spreading, operand packing.
@@ -208,6 +213,9 @@ int hs_gemm_planes(int32_t kind, const void* A, int64_t lda, const void* B, int6
  * chunk_kb K-blocks of 64 elements (default 8): error <= 4*chunk_kb*2^-23 per output,
  * independent of K.  Tuning/diagnostic knob. */
 int hs_gemm_config(int32_t chunk_kb);
+/* 1 (default): CTA-pair kernel (tcgen05 cta_group::2, UMMA M=256, each CTA stages half of B);
+ * 0: single-CTA kernel (M=128).  Results are bit-identical. */
+int hs_gemm_use_cta_pair(int32_t on);
 /* Plain CUDA-core fp32-accumulate version of the same contract, used by the GPU tests as
  * an on-device cross-check of the tcgen05 path (never by the product path). */
 int hs_gemm_planes_simt(int32_t kind, const void* A, int64_t lda, const void* B,

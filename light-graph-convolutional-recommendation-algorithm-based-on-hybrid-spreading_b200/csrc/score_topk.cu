@@ -81,18 +81,21 @@ __global__ void seen_fill_kernel(const int32_t* __restrict__ seen_ptr, const int
 }
 
 // ------------------------------------------------------------------------------------------
-// row-wise masked top-k: radix select on the 64-bit composite key (ordered fp32 value, index)
+// row-wise masked top-k on the 64-bit composite key (ordered fp32 value, column index)
 // ------------------------------------------------------------------------------------------
-// One CTA per row.  The row is read from global memory ONCE (when it has <= 256*RCACHE columns)
-// into per-thread registers as order-preserving 32-bit keys with the exclusion applied.  MSB-first
-// 11-bit digits of the composite key are histogrammed until the undecided bucket plus everything
-// above it fits a 256-entry candidate buffer, which is then sorted (bitonic) — typically two
-// digit passes for continuous scores, six only when the whole row ties.  Exact and deterministic;
-// equal values rank the LARGER index first (np.argsort(row)[::-1] / CPU torch.topk order).
-constexpr int kTopkThreads = 256;
+// ONE WARP per row, k <= 128 << n_cols, no shared memory and no barriers.  Each lane streams its
+// strided share of the row once (coalesced 128 B per warp load, evict-first, 8 loads in flight)
+// and keeps a sorted list of its LIST largest (value key, column) pairs.  The hot loop is one
+// 32-bit compare per element: only values that beat the lane's current LIST-th best go on to the
+// exclusion test (one bit of the bit-packed rows x n_cols mask) and the insertion.  Then k rounds
+// of a warp-wide arg-max over the list heads — two REDUX instructions (value, then column among
+// the equal values) — pop the winners in final order.  A lane whose list runs dry re-streams its
+// share below its last popped pair, so the result is exact for any distribution.  (value, column)
+// pairs are unique, so the result is deterministic and equal values rank the LARGER column first
+// (np.argsort(row)[::-1] order).  If fewer than k columns are selectable the tail is -1.
+constexpr int kTopkWarps = 8;
 constexpr int kTopkMaxK = 128;
-constexpr int kCand = 256;
-constexpr int kBins = 2048;
+constexpr int kTopkUnroll = 8;
 
 __device__ __forceinline__ uint32_t float_key(float x) {
   const uint32_t b = __float_as_uint(x);
@@ -102,169 +105,99 @@ __device__ __forceinline__ float key_float(uint32_t k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-struct TopkSmem {
-  unsigned int hist[kBins];
-  unsigned long long cand[kCand];
-  unsigned int warp_tot[kTopkThreads / 32];
-  unsigned long long prefix;  // decided high bits of the k-th largest key (low bits zero)
-  int k_rem;                  // how many are still to be taken from the undecided bucket
-  int n_above;                // elements strictly above the undecided bucket (all selected)
-  int n_eq;                   // elements in the undecided bucket
-  int n_cand;
-};
-
-template <int RCACHE>
-__global__ void __launch_bounds__(kTopkThreads)
-topk_rows_kernel(const float* __restrict__ S, int64_t n_cols, int64_t lds, const int32_t* __restrict__ excl_ptr,
-                 const int32_t* __restrict__ excl_idx, int64_t row_offset, int k, int64_t* __restrict__ out_idx,
+template <int LIST>
+__global__ void __launch_bounds__(kTopkWarps * 32)
+topk_rows_kernel(const float* __restrict__ S, int n_rows, int n, int64_t lds, const uint32_t* __restrict__ mask,
+                 int64_t mask_stride_bits, int64_t row_offset, int k, int64_t* __restrict__ out_idx,
                  float* __restrict__ out_val) {
-  extern __shared__ unsigned int s_dyn[];
-  __shared__ TopkSmem sm;
-  unsigned int* bitmap = s_dyn;  // n_cols bits: 1 = excluded
-  const int64_t r = blockIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * kTopkWarps + (threadIdx.x >> 5);
+  if (r >= n_rows) return;
   const float* row = S + r * lds;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n = (int)n_cols;
-  const int words = (n + 31) / 32;
+  const int64_t bit0 = (row_offset + r) * mask_stride_bits;
+  const uint32_t* mrow = mask ? mask + (bit0 >> 5) : nullptr;
+  const uint32_t boff = (uint32_t)(bit0 & 31);
 
-  for (int w = tid; w < words; w += kTopkThreads) bitmap[w] = 0u;
-  if (tid == 0) { sm.prefix = 0ull; sm.k_rem = k; sm.n_above = 0; sm.n_eq = n; sm.n_cand = 0; }
-  __syncthreads();
-  if (excl_ptr) {
-    const int s = excl_ptr[row_offset + r], e = excl_ptr[row_offset + r + 1];
-    for (int i = s + tid; i < e; i += kTopkThreads) {
-      const int c = excl_idx[i];
-      if (c >= 0 && c < n) atomicOr(&bitmap[c >> 5], 1u << (c & 31));
-    }
-  }
-  __syncthreads();
-
-  auto load_key = [&](int c) -> uint32_t {  // excluded columns get key 0 (below every real value)
-    const bool ex = (bitmap[c >> 5] >> (c & 31)) & 1u;
-    return ex ? 0u : float_key(__ldg(row + c));
-  };
-  uint32_t kreg[RCACHE > 0 ? RCACHE : 1];
-  if (RCACHE > 0) {
+  uint32_t lv[LIST], lc[LIST];  // value keys / column+1, sorted descending; lc == 0 marks an empty slot
+  // keep the LIST largest pairs strictly below (bv, bc) among this lane's columns (ascending column order,
+  // so among equal values the later column is the larger pair)
+  auto stream = [&](uint32_t bv, uint32_t bc) {
 #pragma unroll
-    for (int i = 0; i < RCACHE; ++i) {
-      const int c = tid + i * kTopkThreads;
-      kreg[i] = c < n ? load_key(c) : 0u;
-    }
-  }
-  // visit every column of the row: f(column, composite key)
-  auto for_each = [&](auto&& f) {
-    if (RCACHE > 0) {
+    for (int i = 0; i < LIST; ++i) { lv[i] = 0u; lc[i] = 0u; }
+    for (int c0 = lane; c0 < n; c0 += 32 * kTopkUnroll) {
+      float v[kTopkUnroll];
 #pragma unroll
-      for (int i = 0; i < RCACHE; ++i) {
-        const int c = tid + i * kTopkThreads;
-        f(c, c < n, ((unsigned long long)kreg[i] << 32) | (unsigned int)c);
+      for (int u = 0; u < kTopkUnroll; ++u) {
+        const int c = c0 + 32 * u;
+        v[u] = c < n ? __ldcs(row + c) : 0.f;
       }
-    } else {
-      for (int c0 = 0; c0 < n; c0 += kTopkThreads) {
-        const int c = c0 + tid;
-        f(c, c < n, c < n ? (((unsigned long long)load_key(c) << 32) | (unsigned int)c) : 0ull);
-      }
-    }
-  };
-
-  // digit schedule over the 64-bit composite key: 11 + 11 + 10 value bits, then the index bits
-  int idx_bits = 1;
-  while ((1 << idx_bits) < n) ++idx_bits;
-  int shift = 64;
-  for (int pass = 0; pass < 8; ++pass) {
-    if (sm.n_above + sm.n_eq <= kCand) break;  // block-uniform (read after a barrier)
-    int width;
-    if (shift > 32) width = shift == 64 ? 11 : shift == 53 ? 11 : 10;
-    else {
-      const int top = shift == 32 ? idx_bits : shift;  // index bits above idx_bits are always zero
-      if (shift == 32) shift = idx_bits;
-      width = top < 11 ? top : 11;
-    }
-    if (width <= 0) break;
-    shift -= width;
-    for (int b = tid; b < kBins; b += kTopkThreads) sm.hist[b] = 0u;
-    __syncthreads();
-    const unsigned long long prefix = sm.prefix;
-    const unsigned long long hi_mask = (shift + width) >= 64 ? 0ull : (~0ull << (shift + width));
-    const unsigned int dmask = (1u << width) - 1u;
-    for_each([&](int, bool valid, unsigned long long key) {
-      const bool act = valid && (key & hi_mask) == prefix;
-      const unsigned int dg = (unsigned int)(key >> shift) & dmask;
-      const unsigned int amask = __ballot_sync(0xffffffffu, act);
-      if (act) {
-        const unsigned int peers = __match_any_sync(amask, dg);
-        if (lane == __ffs(peers) - 1) atomicAdd(&sm.hist[dg], (unsigned int)__popc(peers));
-      }
-    });
-    __syncthreads();
-    // find the bucket holding the k_rem-th largest: descending scan over the bins
-    constexpr int PER = kBins / kTopkThreads;  // 8 bins per thread, thread 0 owns the TOP bins
-    unsigned int mine = 0;
 #pragma unroll
-    for (int i = 0; i < PER; ++i) mine += sm.hist[kBins - 1 - (tid * PER + i)];
-    unsigned int incl = mine;
+      for (int u = 0; u < kTopkUnroll; ++u) {
+        const int c = c0 + 32 * u;
+        const uint32_t vk = float_key(v[u]);
+        // fast reject: not better than this lane's LIST-th best (an empty slot has lv == 0)
+        if (c < n && (vk >= lv[LIST - 1] || lc[LIST - 1] == 0u)) {
+          const bool below = vk < bv || (vk == bv && (uint32_t)(c + 1) < bc);
+          bool ex = false;
+          if (mrow) {
+            const uint32_t b = boff + (uint32_t)c;
+            ex = (__ldg(mrow + (b >> 5)) >> (b & 31)) & 1u;
+          }
+          if (below && !ex) {
+            lv[LIST - 1] = vk;
+            lc[LIST - 1] = (uint32_t)(c + 1);
+            bool moving = true;  // bubble the new pair up; it stops at the first strictly larger value
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const unsigned int t = __shfl_up_sync(0xffffffffu, incl, off);
-      if (lane >= off) incl += t;
-    }
-    if (lane == 31) sm.warp_tot[warp] = incl;
-    __syncthreads();
-    unsigned int before = 0;
-    for (int w = 0; w < warp; ++w) before += sm.warp_tot[w];
-    const unsigned int excl_sum = before + incl - mine;  // elements in bins above this thread's bins
-    const unsigned int k_rem = (unsigned int)sm.k_rem;
-    __syncthreads();
-    if (excl_sum < k_rem && excl_sum + mine >= k_rem) {  // exactly one thread
-      unsigned int acc = excl_sum;
-      for (int i = 0; i < PER; ++i) {
-        const int bin = kBins - 1 - (tid * PER + i);
-        const unsigned int cnt = sm.hist[bin];
-        if (acc + cnt >= k_rem) {
-          sm.prefix = prefix | ((unsigned long long)bin << shift);
-          sm.k_rem = (int)(k_rem - acc);
-          sm.n_above += (int)acc;
-          sm.n_eq = (int)cnt;
-          break;
+            for (int i = LIST - 1; i > 0; --i) {
+              moving = moving && (lc[i - 1] == 0u || lv[i] >= lv[i - 1]);
+              if (moving) {
+                const uint32_t tv = lv[i], tc = lc[i];
+                lv[i] = lv[i - 1]; lc[i] = lc[i - 1];
+                lv[i - 1] = tv; lc[i - 1] = tc;
+              }
+            }
+          }
         }
-        acc += cnt;
       }
     }
-    __syncthreads();
-  }
-  // everything >= prefix (at the decided precision) is a candidate: n_above + n_eq <= kCand of them,
-  // or exactly k when all digits were consumed
-  {
-    const unsigned long long thr = sm.prefix;
-    for_each([&](int, bool valid, unsigned long long key) {
-      if (valid && key >= thr) {
-        const int pos = atomicAdd(&sm.n_cand, 1);
-        if (pos < kCand) sm.cand[pos] = key;
-      }
-    });
-  }
-  __syncthreads();
-  const int n_cand = min(sm.n_cand, kCand);
-  int sort_n = 32;
-  while (sort_n < n_cand) sort_n <<= 1;
-  for (int i = n_cand + tid; i < sort_n; i += kTopkThreads) sm.cand[i] = 0ull;
-  __syncthreads();
-  for (int size = 2; size <= sort_n; size <<= 1) {  // bitonic sort, descending
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      if (tid < sort_n / 2) {
-        const int lo = 2 * tid - (tid & (stride - 1));
-        const int hi = lo + stride;
-        const bool desc = ((lo & size) == 0);
-        const unsigned long long a = sm.cand[lo], b = sm.cand[hi];
-        if ((a < b) == desc) { sm.cand[lo] = b; sm.cand[hi] = a; }
-      }
-      __syncthreads();
+  };
+  stream(0xffffffffu, 0xffffffffu);
+
+  for (int round = 0; round < k; ++round) {
+    const bool has = lc[0] != 0u;
+    const uint32_t mv = __reduce_max_sync(0xffffffffu, has ? lv[0] : 0u);
+    const uint32_t mc = __reduce_max_sync(0xffffffffu, (has && lv[0] == mv) ? lc[0] : 0u);
+    if (mc == 0u) {  // fewer than k selectable columns
+      if (lane == 0)
+        for (int t = round; t < k; ++t) {
+          out_idx[r * k + t] = -1;
+          if (out_val) out_val[r * k + t] = -INFINITY;
+        }
+      break;
+    }
+    if (has && lv[0] == mv && lc[0] == mc) {  // exactly one lane
+      out_idx[r * k + round] = (int64_t)(mc - 1u);
+      if (out_val) out_val[r * k + round] = key_float(mv);
+#pragma unroll
+      for (int i = 0; i < LIST - 1; ++i) { lv[i] = lv[i + 1]; lc[i] = lc[i + 1]; }
+      lv[LIST - 1] = 0u; lc[LIST - 1] = 0u;
+      if (lc[0] == 0u) stream(mv, mc);  // list ran dry: refill with this lane's pairs below the popped one
     }
   }
-  if (tid < k) {
-    const unsigned long long key = sm.cand[tid];
-    out_idx[r * k + tid] = (int64_t)(unsigned int)(key & 0xffffffffull);
-    if (out_val) out_val[r * k + tid] = key_float((uint32_t)(key >> 32));
+}
+
+// bit-packed exclusion mask from a CSR (row r, column c -> bit r*stride + c), mask zero-filled by the caller
+__global__ void mask_from_csr_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx, int64_t n_rows,
+                                     int64_t n_cols, int64_t stride_bits, uint32_t* __restrict__ mask) {
+  const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / 32;
+  const int lane = threadIdx.x & 31;
+  if (r >= n_rows) return;
+  for (int i = ptr[r] + lane; i < ptr[r + 1]; i += 32) {
+    const int c = idx[i];
+    if (c >= 0 && c < n_cols) {
+      const int64_t b = r * stride_bits + c;
+      atomicOr(mask + (b >> 5), 1u << (b & 31));
+    }
   }
 }
 
@@ -295,32 +228,32 @@ extern "C" int lgc_score_block(const float* Xu, const float* Xi, int64_t u0, int
   return LGC_OK;
 }
 
-extern "C" int lgc_topk_rows(const float* S, int64_t n_rows, int64_t n_cols, int64_t lds,
-                             const int32_t* excl_ptr, const int32_t* excl_idx, int64_t row_offset, int32_t k,
-                             int64_t* out_idx, float* out_val, lgc_stream_t stream) {
+extern "C" int lgc_topk_rows(const float* S, int64_t n_rows, int64_t n_cols, int64_t lds, const uint32_t* excl_mask,
+                             int64_t mask_stride_bits, int64_t row_offset, int32_t k, int64_t* out_idx,
+                             float* out_val, lgc_stream_t stream) {
   LGC_REQUIRE(S && out_idx, "topk: null pointer");
   LGC_REQUIRE(n_rows > 0 && n_cols > 0 && lds >= n_cols, "topk: bad extents");
   LGC_REQUIRE(k >= 1 && k <= kTopkMaxK && k <= n_cols, "topk: k must be in [1, min(128, n_cols)]");
-  LGC_REQUIRE(n_cols < (1ll << 31) && n_rows < (1ll << 31), "topk: extents exceed int32");
-  LGC_REQUIRE((excl_ptr == nullptr) == (excl_idx == nullptr), "topk: excl_ptr / excl_idx mismatch");
-  const size_t dyn = (size_t)((n_cols + 31) / 32) * sizeof(unsigned int);
-  LGC_REQUIRE(dyn <= 160 * 1024, "topk: more than 1.3M columns per row is not supported");
+  LGC_REQUIRE(n_cols < (1ll << 31) - 1 && n_rows < (1ll << 31), "topk: extents exceed int32");
+  LGC_REQUIRE(!excl_mask || mask_stride_bits >= n_cols, "topk: mask stride smaller than the row");
+  LGC_REQUIRE(((uintptr_t)excl_mask & 3) == 0, "topk: mask must be 4-byte aligned");
+  const unsigned grid = (unsigned)ceil_div(n_rows, kTopkWarps);
   cudaStream_t st = (cudaStream_t)stream;
-#define LGC_TOPK_LAUNCH(RC)                                                                                  \
-  do {                                                                                                       \
-    static size_t dyn_set = 32 * 1024;                                                                       \
-    if (dyn > dyn_set) {                                                                                     \
-      LGC_CUDA(cudaFuncSetAttribute(topk_rows_kernel<RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
-      dyn_set = dyn;                                                                                         \
-    }                                                                                                        \
-    topk_rows_kernel<RC><<<(unsigned)n_rows, kTopkThreads, dyn, st>>>(S, n_cols, lds, excl_ptr, excl_idx,    \
-                                                                      row_offset, k, out_idx, out_val);      \
-  } while (0)
-  if (n_cols <= 8 * kTopkThreads) LGC_TOPK_LAUNCH(8);
-  else if (n_cols <= 16 * kTopkThreads) LGC_TOPK_LAUNCH(16);
-  else if (n_cols <= 32 * kTopkThreads) LGC_TOPK_LAUNCH(32);
-  else LGC_TOPK_LAUNCH(0);
-#undef LGC_TOPK_LAUNCH
+  if (k <= 32)
+    topk_rows_kernel<4><<<grid, kTopkWarps * 32, 0, st>>>(S, (int)n_rows, (int)n_cols, lds, excl_mask, mask_stride_bits,
+                                                          row_offset, k, out_idx, out_val);
+  else
+    topk_rows_kernel<8><<<grid, kTopkWarps * 32, 0, st>>>(S, (int)n_rows, (int)n_cols, lds, excl_mask, mask_stride_bits,
+                                                          row_offset, k, out_idx, out_val);
   LGC_LAUNCH_CHECK("topk_rows_kernel");
+  return LGC_OK;
+}
+
+extern "C" int lgc_mask_from_csr(const int32_t* ptr, const int32_t* idx, int64_t n_rows, int64_t n_cols,
+                                 int64_t stride_bits, uint32_t* mask, lgc_stream_t stream) {
+  LGC_REQUIRE(ptr && idx && mask && n_rows > 0 && n_cols > 0 && stride_bits >= n_cols, "mask_from_csr: bad arguments");
+  mask_from_csr_kernel<<<(unsigned)ceil_div(n_rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(ptr, idx, n_rows, n_cols,
+                                                                                              stride_bits, mask);
+  LGC_LAUNCH_CHECK("mask_from_csr_kernel");
   return LGC_OK;
 }

@@ -26,119 +26,10 @@
 //                               per stage into a double-buffered TMEM accumulator (2 x 256 col)
 //   warps 2..5  epilogue      : tcgen05.ld 32x32b -> combine planes -> scale -> fp32 store,
 //                               overlapped with the next tile's main loop
-#include <cuda.h>
-
-#include "common.cuh"
+#include "umma_common.cuh"
 
 namespace lgc {
 namespace umma {
-
-constexpr int kBlockM = 128;
-constexpr int kKBytes = 128;  // bytes of K per stage = one 128B swizzle atom
-constexpr int kStages = 4;
-constexpr int kAStage = kBlockM * kKBytes;  // 16 KB
-constexpr int kBStage = 256 * kKBytes;      // 32 KB (N <= 256 rows)
-constexpr int kStageBytes = kAStage + kBStage;
-constexpr int kThreads = 192;
-constexpr int kTmemCols = 512;
-constexpr int kAccStride = 256;
-constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must trap (sticky CUDA error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) {  // ~2 s at 2 GHz
-      printf("lgcnhs umma_gemm: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
-                                            int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
-//   start address >> 4 | LBO (unused for swizzled K-major) | SBO = 8 rows * 128 B = 1024 B
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-
-template <int KIND>
-__device__ __forceinline__ void mma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                       uint32_t accumulate) {
-  if (KIND == 0) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-  }
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 struct GemmParams {
   int64_t M, N;      // output rows, output columns (per plane)
@@ -328,6 +219,277 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
   }
 }
 
+
+// ================================================================================================
+// CTA-pair variant (tcgen05 cta_group::2, cluster of two CTAs on one TPC, UMMA M = 256).
+// The single-CTA kernel above is shared-memory-bandwidth bound: per K-block TMA writes 46 KB and
+// the MMA reads 46 KB of smem in 480 cycles = 192 B/clk against the 128 B/clk port (tensor pipe
+// 67-71 % measured, profiles/r1_ncu_gemm.txt).  Here each CTA stages its own 128 rows of A but only
+// HALF of the B rows (N/2); the pair's tensor cores read both halves, so per-CTA smem traffic drops
+// to 2 x 31 KB per 480 cycles = 129 B/clk.
+//   * both CTAs run a TMA producer; all transaction bytes are signalled on the LEADER's (even CTA)
+//     full barrier (barrier address with the peer bit cleared), count 2: leader arrive.expect_tx +
+//     one remote arrive from the peer producer;
+//   * only the leader's warp 1 issues MMAs; tcgen05.commit multicasts the "stage free" and
+//     "accumulator full" arrivals to both CTAs;
+//   * both CTAs run 4 epilogue warps on their own 128 TMEM lanes and arrive remotely on the leader's
+//     "accumulator empty" barrier (count 8).
+// ================================================================================================
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared::cluster address of the even CTA of a pair
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // remote (or local) arrive on the even CTA
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit2_mc(uint64_t* bar) {  // arrive on the same barrier offset in BOTH CTAs
+  const unsigned short mask = 3;
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+template <int KIND>
+__device__ __forceinline__ void mma2_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  if (KIND == 0) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+
+// each CTA stages 16 KB of A + <= 16 KB of B per K-block, so six stages fit where the single-CTA kernel has four
+constexpr int kPStages = 6;
+constexpr int kPBStage = 128 * kKBytes;  // 16 KB
+constexpr int kPStageBytes = kAStage + kPBStage;
+static_assert((size_t)kPStages * kPStageBytes <= (size_t)kStages * kStageBytes, "pair pipeline must fit the same smem budget");
+
+template <int KIND, int PLANES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
+                      const __grid_constant__ CUtensorMap tmapBh, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smemA = smem;
+  uint8_t* smemB = smem + kPStages * kAStage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPStages * kPStageBytes);
+  uint64_t* full = bars;                      // [kStages]  used on the leader
+  uint64_t* empty = bars + kPStages;           // [kStages]  per CTA
+  uint64_t* tfull = bars + 2 * kPStages;       // [2]        per CTA
+  uint64_t* tempty = bars + 2 * kPStages + 2;  // [2]        used on the leader
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  constexpr int NB = PLANES == 3 ? 80 : PLANES == 4 ? 64 : 128;  // output columns per tile
+  constexpr int n_mma = PLANES * NB;                              // MMA N (both halves)
+  constexpr int H = n_mma / 2;                                    // B rows staged by each CTA
+  const int num_tiles = p.tiles_m * p.tiles_n;                    // tiles_m counts 256-row tiles here
+  const int n_chunks = (p.num_kb + p.chunk_kb - 1) / p.chunk_kb;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kPStages; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapBh) : "memory");
+  }
+  cluster_sync_all();  // the peer's barriers are initialised before any remote arrive / multicast commit
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (both CTAs) ------------------------------
+    if (lane == 0) {
+      const uint32_t cta_tx = (uint32_t)(kAStage + H * kKBytes);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = cluster_id; t < num_tiles; t += n_clusters) {
+        const int m_blk = t % p.tiles_m, n_blk = t / p.tiles_m;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (leader) mbar_expect_tx(&full[stage], 2 * cta_tx);
+          else mbar_arrive_leader(&full[stage]);
+          const int k0 = kb * p.k_elems_per_kb;
+          tma2_load_2d(&tmapA, &full[stage], smemA + stage * kAStage, k0, m_blk * 256 + (int)rank * kBlockM);
+          // this CTA's half of the stacked plane rows [rank*H, rank*H + H)
+          uint8_t* dstB = smemB + stage * kPBStage;
+          if (PLANES == 3) {
+            if (leader) {
+              tma2_load_3d(&tmapB, &full[stage], dstB, k0, n_blk * NB, 0);
+              tma2_load_3d(&tmapBh, &full[stage], dstB + NB * kKBytes, k0, n_blk * NB, 1);
+            } else {
+              tma2_load_3d(&tmapBh, &full[stage], dstB, k0, n_blk * NB + NB / 2, 1);
+              tma2_load_3d(&tmapB, &full[stage], dstB + (NB / 2) * kKBytes, k0, n_blk * NB, 2);
+            }
+          } else if (PLANES == 1) {
+            tma2_load_3d(&tmapBh, &full[stage], dstB, k0, n_blk * NB + (int)rank * (NB / 2), 0);
+          } else {
+#pragma unroll
+            for (int q = 0; q < PLANES / 2; ++q)
+              tma2_load_3d(&tmapB, &full[stage], dstB + q * NB * kKBytes, k0, n_blk * NB, (int)rank * (PLANES / 2) + q);
+          }
+          if (++stage == kPStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer (leader CTA only) ------------------------------
+    if (leader) {
+      uint32_t idesc = 0;
+      if (KIND == 0) idesc |= (1u << 4) | (1u << 7) | (1u << 10);
+      else idesc |= (2u << 4);
+      idesc |= ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = cluster_id; t < num_tiles; t += n_clusters) {
+        for (int ch = 0; ch < n_chunks; ++ch, ++it) {
+          const int acc = it & 1;
+          const uint32_t acc_phase = (it >> 1) & 1;
+          mbar_wait(&tempty[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * kAccStride;
+          const int kb0 = ch * p.chunk_kb;
+          const int kb1 = min(kb0 + p.chunk_kb, p.num_kb);
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            if (lane == 0) {
+              const uint64_t adesc = make_smem_desc(smem_u32(smemA + stage * kAStage));
+              const uint64_t bdesc = make_smem_desc(smem_u32(smemB + stage * kPBStage));
+#pragma unroll
+              for (int k = 0; k < kKBytes / 32; ++k)
+                mma2_ss<KIND>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
+              tc_commit2_mc(&empty[stage]);
+              if (kb == kb1 - 1) tc_commit2_mc(&tfull[acc]);
+            }
+            __syncwarp();
+            if (++stage == kPStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (warps 2..5, both CTAs) ------------------------------
+    const int q = warp & 3;
+    int it = 0;
+    for (int t = cluster_id; t < num_tiles; t += n_clusters) {
+      const int m_blk = t % p.tiles_m, n_blk = t / p.tiles_m;
+      const int64_t row = (int64_t)m_blk * 256 + (int64_t)rank * kBlockM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const float rscale = (row_ok && p.rs) ? __ldg(p.rs + row) : 1.0f;
+      float* crow = p.C + (row_ok ? row : 0) * p.ldc;
+      float run[NB];
+      for (int ch = 0; ch < n_chunks; ++ch, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride;
+        const bool first = ch == 0, last = ch == n_chunks - 1;
+#pragma unroll
+        for (int c0 = 0; c0 < NB; c0 += 16) {
+          uint32_t r[PLANES][16];
+#pragma unroll
+          for (int pl = 0; pl < PLANES; ++pl) tmem_ld16(t_row + pl * NB + c0, r[pl]);
+          tmem_ld_wait();
+          float out[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (KIND == 0) {
+              float a = __uint_as_float(r[PLANES - 1][j]);
+#pragma unroll
+              for (int pl = PLANES - 2; pl >= 0; --pl) a += __uint_as_float(r[pl][j]);
+              if (!first) a += run[c0 + j];
+              run[c0 + j] = a;
+              out[j] = a * (float)p.scale;
+            } else {
+              long long tot = 0;
+#pragma unroll
+              for (int pl = PLANES - 1; pl >= 0; --pl) tot = (tot << 8) + (long long)(int)r[pl][j];
+              out[j] = (float)((double)tot * p.scale);
+            }
+          }
+          if (last) {
+            const int64_t col0 = (int64_t)n_blk * NB + c0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int64_t col = col0 + j;
+              const float cscale = (p.cs && col < p.N) ? __ldg(p.cs + col) : 1.0f;
+              out[j] = out[j] * rscale * cscale;
+            }
+            if (row_ok) {
+              if (col0 + 16 <= p.N && (p.ldc & 3) == 0 && ((uintptr_t)p.C & 15) == 0) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                  *reinterpret_cast<float4*>(crow + col0 + j) = make_float4(out[j], out[j + 1], out[j + 2], out[j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (col0 + j < p.N) crow[col0 + j] = out[j];
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tempty[acc]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // neither CTA may exit (or free TMEM) while the other can still touch its smem/TMEM
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols)
+                 : "memory");
+  }
+}
+
+static int g_use_pair = 1;   // cta_group::2 kernel when the problem has at least one 256-row tile
 static int g_chunk_kb = 8;  // K-blocks (of 64 bf16) per TMEM accumulation chunk, see header comment
 
 // ---- host side: tensor maps through the driver entry point (no -lcuda link dependency) ----
@@ -445,9 +607,45 @@ extern "C" int hs_gemm_planes(int32_t kind, const void* A, int64_t lda, const vo
   p.C = C; p.ldc = ldc; p.rs = rs; p.cs = cs; p.scale = scale;
   p.k_elems_per_kb = k_elems;
   p.chunk_kb = kind == 0 ? g_chunk_kb : p.num_kb;  // int32 accumulation is exact: one chunk
+  cudaStream_t stream = (cudaStream_t)stream_;
+
+  if (g_use_pair && M > kBlockM) {
+    // CTA-pair kernel: 256-row tiles, each CTA stages half of the stacked plane rows of B
+    CUtensorMap tmBh;
+    {
+      cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, (cuuint64_t)planes};
+      cuuint64_t strides[2] = {(cuuint64_t)ldb * esize, (cuuint64_t)(planes > 1 ? plane_stride : N * ldb) * esize};
+      cuuint32_t box[3] = {(cuuint32_t)k_elems, (cuuint32_t)(NB / 2), 1};
+      cuuint32_t estr[3] = {1, 1, 1};
+      CUresult r = encode(&tmBh, dt, 3, const_cast<void*>(B), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) LGC_FAIL(LGC_ERR_CUDA, "gemm: cuTensorMapEncodeTiled(B half) failed with %d", (int)r);
+    }
+    p.tiles_m = (int)ceil_div(M, 256);
+    const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
+    int clusters = num_sms() / 2;
+    if (tiles < clusters) clusters = (int)tiles;
+    const int grid = 2 * clusters;
+#define LGC_GEMM_PAIR_CASE(KD, PL)                                                                              \
+  if (kind == KD && planes == PL) {                                                                             \
+    static bool attr = false;                                                                                   \
+    if (!attr) {                                                                                                \
+      LGC_CUDA(cudaFuncSetAttribute(umma_gemm_pair_kernel<KD, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    (int)kSmemBytes));                                                          \
+      attr = true;                                                                                              \
+    }                                                                                                           \
+    umma_gemm_pair_kernel<KD, PL><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmBh, p);                   \
+  }
+    LGC_GEMM_PAIR_CASE(0, 1) LGC_GEMM_PAIR_CASE(0, 2) LGC_GEMM_PAIR_CASE(0, 3)
+    LGC_GEMM_PAIR_CASE(1, 1) LGC_GEMM_PAIR_CASE(1, 2) LGC_GEMM_PAIR_CASE(1, 4)
+#undef LGC_GEMM_PAIR_CASE
+    LGC_LAUNCH_CHECK("umma_gemm_pair_kernel");
+    return LGC_OK;
+  }
+
   const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  cudaStream_t stream = (cudaStream_t)stream_;
 #define LGC_GEMM_CASE(KD, PL)                                                                             \
   if (kind == KD && planes == PL) {                                                                       \
     static bool attr = false;                                                                             \
@@ -462,6 +660,11 @@ extern "C" int hs_gemm_planes(int32_t kind, const void* A, int64_t lda, const vo
   LGC_GEMM_CASE(1, 1) LGC_GEMM_CASE(1, 2) LGC_GEMM_CASE(1, 4)
 #undef LGC_GEMM_CASE
   LGC_LAUNCH_CHECK("umma_gemm_kernel");
+  return LGC_OK;
+}
+
+extern "C" int hs_gemm_use_cta_pair(int32_t on) {
+  g_use_pair = on ? 1 : 0;
   return LGC_OK;
 }
 

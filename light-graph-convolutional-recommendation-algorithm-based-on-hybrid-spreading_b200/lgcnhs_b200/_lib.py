@@ -37,7 +37,8 @@ _SIGS = {
     "lgc_bpr_rows": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i32, _f32, _f32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "lgc_adam_step": (C.c_int, [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _p]),
     "lgc_score_block": (C.c_int, [_p, _p, _i64, _i64, _i64, _i32, _p, _p, _f32, _p, _i64, _p]),
-    "lgc_topk_rows": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _i64, _i32, _p, _p, _p]),
+    "lgc_topk_rows": (C.c_int, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i32, _p, _p, _p]),
+    "lgc_mask_from_csr": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _p]),
     "hs_degrees": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p]),
     "hs_pack_a": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _i64, _p]),
     "hs_pack_at": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _i32, _i32, _p, _p, _i64, _i64, _p]),
@@ -45,6 +46,7 @@ _SIGS = {
     "hs_gemm_planes_simt": (C.c_int, [_i32, _p, _i64, _p, _i64, _i64, _i32, _i64, _i64, _i64, _p, _i64, _p, _p,
                                       _f64, _p]),
     "hs_gemm_config": (C.c_int, [_i32]),
+    "hs_gemm_use_cta_pair": (C.c_int, [_i32]),
     "hs_scale_w": (C.c_int, [_p, _i64, _i64, _p, _f64, _p, _i64, _p, _i64, _i64, _i32, _p]),
     "hs_hadamard": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _p]),
     "lgc_ipc_get_handle": (C.c_int, [_p, _p]),

@@ -223,17 +223,37 @@ def score_block(Xu: torch.Tensor, Xi: torch.Tensor, u0: int, u1: int, seen: Opti
     return out
 
 
-def topk_rows(S: torch.Tensor, k: int, excl: Optional[tuple] = None, row_offset: int = 0,
+class ExclusionMask:
+    """Bit-packed (n_rows x n_cols) matrix of entries that must never be recommended."""
+
+    def __init__(self, bits: torch.Tensor, n_rows: int, n_cols: int, stride_bits: int):
+        self.bits, self.n_rows, self.n_cols, self.stride_bits = bits, n_rows, n_cols, stride_bits
+
+    @staticmethod
+    def from_csr(csr: tuple, n_rows: int, n_cols: int) -> "ExclusionMask":
+        ptr, idx = csr
+        bits = torch.zeros((n_rows * n_cols + 31) // 32, dtype=torch.int32, device=ptr.device)
+        check(lib().lgc_mask_from_csr(_ptr(ptr), _ptr(idx), n_rows, n_cols, n_cols, _ptr(bits), _stream()), "mask from csr")
+        return ExclusionMask(bits, n_rows, n_cols, n_cols)
+
+    @staticmethod
+    def from_pairs(users: torch.Tensor, items: torch.Tensor, n_rows: int, n_cols: int) -> "ExclusionMask":
+        return ExclusionMask.from_csr(seen_csr(users, items, n_rows, n_cols), n_rows, n_cols)
+
+
+def topk_rows(S: torch.Tensor, k: int, excl: Optional[ExclusionMask] = None, row_offset: int = 0,
               want_values: bool = True):
-    S = _req(S, torch.float32, "S") if S.is_contiguous() else S
-    if S.dtype != torch.float32 or not S.is_cuda or S.stride(1) != 1:
+    """Row-wise top-k (sorted, ties -> larger index).  Row r of S is row `row_offset + r` of the mask."""
+    if S.dtype != torch.float32 or not S.is_cuda or S.dim() != 2 or S.stride(1) != 1:
         raise LgcnhsError("topk: S must be a CUDA fp32 matrix with unit column stride")
     rows, cols = int(S.shape[0]), int(S.shape[1])
+    if excl is not None and (excl.n_cols != cols or row_offset + rows > excl.n_rows):
+        raise LgcnhsError("topk: exclusion mask does not cover the score block")
     idx = torch.empty((rows, k), dtype=torch.int64, device=S.device)
     val = torch.empty((rows, k), dtype=torch.float32, device=S.device) if want_values else None
-    ep, ei = (None, None) if excl is None else excl
-    check(lib().lgc_topk_rows(_ptr(S), rows, cols, int(S.stride(0)), _ptr(ep), _ptr(ei), int(row_offset), int(k),
-                              _ptr(idx), _ptr(val), _stream()), "topk rows")
+    check(lib().lgc_topk_rows(_ptr(S), rows, cols, int(S.stride(0)), _ptr(excl.bits) if excl else 0,
+                              excl.stride_bits if excl else 0, int(row_offset), int(k), _ptr(idx), _ptr(val), _stream()),
+          "topk rows")
     return idx, val
 
 
@@ -300,20 +320,14 @@ class SpreadingEngine:
         bitmap = torch.zeros((U * M + 31) // 32, dtype=torch.int32, device=dev)
         check(L.hs_degrees(_ptr(users), _ptr(items), self.nnz, U, M, _ptr(self.ku), _ptr(self.ki), _ptr(bitmap),
                            _stream()), "degrees")
-        del bitmap
+        # the deduplicated bit-packed A doubles as the top-k exclusion mask (train ⊕ val items)
+        self.excl = ExclusionMask(bitmap, U, M, M)
         self.ldM = _pad(M, 64)   # K extent (items) of A and W^T planes, bf16
         self.A = torch.zeros((U, self.ldM), dtype=torch.bfloat16, device=dev)
         check(L.hs_pack_a(_ptr(users), _ptr(items), self.nnz, U, M, _ptr(self.A), self.ldM, _stream()), "pack_a")
         self.G: Optional[torch.Tensor] = None
         self.Wt: Optional[torch.Tensor] = None
-        self._excl = None
 
-    # exclusion CSR (train ⊕ val items of every user) for the filtered top-k
-    @property
-    def excl(self):
-        if self._excl is None:
-            self._excl = seen_csr(self.users, self.items, self.U, self.M)
-        return self._excl
 
     def fixed_point(self) -> tuple[int, int]:
         """(digits, shift) of the base-256 fixed-point 1/k_u: q_u = round(2^shift / k_u) < 256^digits,

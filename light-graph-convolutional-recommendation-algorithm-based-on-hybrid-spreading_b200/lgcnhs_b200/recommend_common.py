@@ -41,7 +41,7 @@ def topk_dict(idx: torch.Tensor, as_array_rows: bool = False) -> dict:
     return out
 
 
-def topk_from_host_matrix(F_new: np.ndarray, k: int, excl: Optional[tuple]) -> torch.Tensor:
+def topk_from_host_matrix(F_new: np.ndarray, k: int, excl: Optional[ops.ExclusionMask]) -> torch.Tensor:
     """Row-wise (filtered) top-k of a HOST matrix: uploaded in user blocks as fp32."""
     dev = cuda_device()
     U, M = F_new.shape

@@ -17,7 +17,7 @@ def recommendForAllUser(F_new: np.ndarray, user_num: int, train_data_df: pd.Data
                         val_data_df: pd.DataFrame, k: int) -> dict:
     """Filtered per-user top-k of a host resource matrix (reference recommend.py:18-52)."""
     u, i = interactions_from_frames(train_data_df, val_data_df)
-    excl = ops.seen_csr(u, i, user_num, F_new.shape[1])
+    excl = ops.ExclusionMask.from_pairs(u, i, user_num, F_new.shape[1])
     out = topk_dict(topk_from_host_matrix(F_new[:user_num], k, excl))
     _save(out)
     return out

@@ -27,7 +27,7 @@ def recommendForAllUser(F_new: np.ndarray, user_num: int, train_data_df: pd.Data
                         val_data_df: pd.DataFrame, k: int) -> dict:
     """Per user: rank items by F_new (descending), drop train+val items, keep k (reference recommend.py:18-56)."""
     u, i = interactions_from_frames(train_data_df, val_data_df)
-    excl = None if _unfiltered() else ops.seen_csr(u, i, user_num, F_new.shape[1])
+    excl = None if _unfiltered() else ops.ExclusionMask.from_pairs(u, i, user_num, F_new.shape[1])
     out = topk_dict(topk_from_host_matrix(F_new[:user_num], k, excl), as_array_rows=_unfiltered())
     _save(out)
     return out

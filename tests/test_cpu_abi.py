@@ -26,7 +26,7 @@ def test_argument_errors_are_reported_not_thrown(lib):
 
     rc = lib.hs_gemm_planes(7, 0, 0, 0, 0, 0, 1, 1, 1, 1, 0, 0, 0, 0, 1.0, 0)
     assert rc == -1 and b"kind" in lib.lgc_last_error_string()
-    rc = lib.lgc_topk_rows(0, 1, 1, 1, 0, 0, 0, 1, 0, 0, 0)
+    rc = lib.lgc_topk_rows(0, 1, 1, 1, 0, 0, 0, 1, 0, 0, 0)  # null score pointer
     assert rc == -1
     with pytest.raises(LgcnhsError):
         check(lib.lgc_adam_step(0, 0, 0, 0, 0, 0.1, 0.9, 0.999, 1e-8, 0.1, 0.1, 0), "adam")

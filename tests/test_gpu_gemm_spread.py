@@ -120,3 +120,36 @@ def test_fusion_hadamard(dev):
     Fd = F.to(dev)
     check(lib().hs_hadamard(Fd.data_ptr(), G.to(dev).data_ptr(), 100, 333, 333, 333, torch.cuda.current_stream().cuda_stream))
     assert torch.equal(Fd.cpu(), F * G)
+
+
+@pytest.mark.parametrize("kind,planes,M,N,K", [(0, 3, 700, 500, 2000), (0, 2, 257, 300, 640), (0, 1, 512, 130, 200),
+                                               (1, 4, 900, 333, 5000), (1, 2, 300, 300, 300), (1, 1, 256, 64, 128)])
+def test_gemm_cta_pair_equals_single_cta(dev, kind, planes, M, N, K):
+    """The cta_group::2 kernel (UMMA M=256, half of B per CTA) must reproduce the single-CTA kernel bit for bit."""
+    from lgcnhs_b200 import ops
+    from lgcnhs_b200._lib import check, lib
+
+    g = torch.Generator().manual_seed(kind * 100 + planes)
+    if kind == 0:
+        ld = (K + 63) // 64 * 64
+        A = torch.zeros(M, ld)
+        A[:, :K] = (torch.rand(M, K, generator=g) < 0.2).float()
+        B = torch.zeros(planes, N, ld, dtype=torch.bfloat16)
+        B[:, :, :K] = _split_bf16(torch.rand(N, K, generator=g) * torch.exp(torch.randn(N, K, generator=g) * 2), planes)
+        Ad, Bd = A.to(torch.bfloat16).to(dev), B.to(dev)
+    else:
+        ld = (K + 127) // 128 * 128
+        A = torch.zeros(M, ld, dtype=torch.uint8)
+        A[:, :K] = (torch.rand(M, K, generator=g) < 0.3).to(torch.uint8)
+        B = torch.zeros(planes, N, ld, dtype=torch.uint8)
+        B[:, :, :K] = torch.randint(0, 256, (planes, N, K), generator=g, dtype=torch.uint8)
+        Ad, Bd = A.to(dev), B.to(dev)
+    try:
+        check(lib().hs_gemm_use_cta_pair(0))
+        C1 = ops.gemm_planes(kind, Ad, Bd, M, N, K, scale=0.25).clone()
+        check(lib().hs_gemm_use_cta_pair(1))
+        C2 = ops.gemm_planes(kind, Ad, Bd, M, N, K, scale=0.25)
+        torch.cuda.synchronize()
+    finally:
+        lib().hs_gemm_use_cta_pair(1)
+    assert torch.equal(C1, C2)

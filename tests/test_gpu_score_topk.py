@@ -82,7 +82,7 @@ def test_topk_with_exclusion_matches_reference_loop(dev):
     for u, i in zip(d.users.tolist(), d.items.tolist()):
         seen.setdefault(u, []).append(i)
     ref = S.recommend_loop(F.numpy(), seen, 20)
-    excl = ops.seen_csr(torch.from_numpy(d.users).to(dev), torch.from_numpy(d.items).to(dev), d.n_users, d.n_items)
+    excl = ops.ExclusionMask.from_pairs(torch.from_numpy(d.users).to(dev), torch.from_numpy(d.items).to(dev), d.n_users, d.n_items)
     F32 = F.float()
     idx, val = ops.topk_rows(F32.to(dev), 20, excl)
     idx = idx.cpu().numpy()
@@ -94,3 +94,25 @@ def test_topk_with_exclusion_matches_reference_loop(dev):
         assert np.array_equal(F.numpy()[u, r].astype(np.float32), val.cpu().numpy()[u])   # score at rank
         ok = np.r_[True, fv[u][1:] != fv[u][:-1]] & np.r_[fv[u][1:] != fv[u][:-1], True]
         assert np.array_equal(idx[u][ok], r[ok])                 # ids equal wherever scores are distinct
+
+
+def test_topk_refill_and_mask_offsets(dev):
+    """Adversarial layout: the whole top-k sits in ONE lane's stride (columns = lane mod 32), so the
+    per-lane list must refill many times; plus a mask whose rows start at unaligned bit offsets."""
+    from lgcnhs_b200 import ops
+
+    rows, cols, k = 37, 1000, 100
+    Sm = torch.rand(rows, cols) * 0.01
+    hot = torch.arange(5, cols, 32)[:31]            # all in lane 5's share
+    Sm[:, hot] = 10.0 + torch.rand(rows, hot.numel())
+    g = torch.Generator().manual_seed(1)
+    ex_u = torch.randint(rows + 11, (4000,), generator=g)
+    ex_i = torch.randint(cols, (4000,), generator=g)
+    mask = ops.ExclusionMask.from_pairs(ex_u.to(dev), ex_i.to(dev), rows + 11, cols)
+    for off in (0, 11):
+        idx, val = ops.topk_rows(Sm.to(dev), k, mask, row_offset=off)
+        ref = Sm.clone()
+        sel = (ex_u >= off) & (ex_u < off + rows)
+        ref[ex_u[sel] - off, ex_i[sel]] = -float("inf")
+        rv, ri = torch.topk(ref, k)
+        assert torch.equal(val.cpu(), rv) and torch.equal(torch.gather(ref, 1, idx.cpu()), rv)
