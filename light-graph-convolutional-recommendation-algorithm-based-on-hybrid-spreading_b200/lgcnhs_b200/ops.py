@@ -329,6 +329,15 @@ class SpreadingEngine:
         self.Wt: Optional[torch.Tensor] = None
 
 
+    def excl_items(self, u: int) -> torch.Tensor:
+        """Deduplicated item ids of user u (row u of A), ascending — decoded from the bit-packed mask."""
+        M = self.M
+        b0 = u * M
+        w0, w1 = b0 // 32, (b0 + M + 31) // 32
+        words = self.excl.bits[w0:w1].to(torch.int64) & 0xFFFFFFFF
+        bits = ((words[:, None] >> torch.arange(32, device=words.device)) & 1).flatten()
+        return torch.nonzero(bits[b0 - w0 * 32: b0 - w0 * 32 + M]).flatten()
+
     def fixed_point(self) -> tuple[int, int]:
         """(digits, shift) of the base-256 fixed-point 1/k_u: q_u = round(2^shift / k_u) < 256^digits,
         relative error <= k_max / 2^(shift+1)."""
