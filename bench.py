@@ -234,12 +234,14 @@ def spreading_leg(dev, steps: int, warmup: int):
     return {
         "workload": f"hybrid spreading ml-1m shape ({U}x{M}, nnz(A)={sel.size}), top-20 full-rank filtered",
         "g_build": {"ms": round(t_g * 1e3, 4), "tflops": round(flops / t_g / 1e12, 2), "kind": "u8 x4 digits, exact"},
-        "f_gemm": {"ms": round(t_f * 1e3, 4), "tflops": round(flops / t_f / 1e12, 2), "kind": "bf16 x3 planes"},
+        "f_gemm": {"ms": round(t_f * 1e3, 4), "tflops": round(flops / t_f / 1e12, 2),
+                   "kind": "u8 x4 digit planes of per-column fixed-point W, exact int32 accumulate (w_mode u8x4)"},
         "lambda_step": {"ms": round(t_step * 1e3, 4), "users_per_s": round(U / t_step, 1),
                         "what": "scale_w + F=A.W + filtered top-20, per lambda"},
         "roofline": {"bound": "tensor", "achieved": round(flops / t_f / 1e12, 2), "peak": peak_burst,
                      "unit": "TFLOP/s", "frac": round(flops / t_f / 1e12 / peak_burst, 4), "traffic": None,
-                     "note": f"useful flops 2*U*M^2 of F=A.W (one pass counted, 3 bf16 planes issued) / {how} bf16 peak"},
+                     "note": f"useful flops 2*U*M^2 of F=A.W (one pass counted; 4 int8 digit planes issued = 2 bf16-pass "
+                             f"equivalents) / {how} bf16 dense peak"},
     }
 
 

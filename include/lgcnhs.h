@@ -197,7 +197,7 @@ int hs_pack_at(const int32_t* users, const int32_t* items, int64_t nnz, int64_t 
  *     C[m, n] = rs[m] * cs[n] * scale * sum_p w_p * sum_k A[m,k] * B_p[n,k]
  * A: (M x K) K-major, B_p: `planes` matrices (N x K) K-major, plane stride in elements.
  * kind 0: bf16 operands, fp32 accumulate, w_p = 1                (planes in {1,2,3})
- * kind 1: uint8 operands, exact int32 accumulate, w_p = 256^p    (planes in {1,2,4})
+ * kind 1: uint8 operands, exact int32 accumulate, w_p = 256^p    (planes in {1,2,3,4})
  * Tile: 128 rows x NB columns x all planes in one MMA (N = planes*NB: 128, 256, 240, 256).
  * Replaces np.dot(A.T / user_degrees, A) (model/SpreadMethod/model.py:25) and
  * np.dot(F0, W) (model/SpreadMethod/model.py:98).
@@ -234,6 +234,18 @@ int hs_gemm_planes_simt(int32_t kind, const void* A, int64_t lda, const void* B,
 int hs_scale_w(const float* G, int64_t ldg, int64_t n, const int32_t* ki, double lambda,
                float* W32, int64_t ldw, uint16_t* Wt_planes, int64_t ldk,
                int64_t plane_stride, int32_t planes, lgc_stream_t stream);
+
+/* HybridS scaling with a FIXED-POINT result for the exact int8 F = A.W GEMM: per column j,
+ * q[i,j] = round(W[i,j] / s_j * 256^digits) with s_j the power of two strictly above max_i W[i,j];
+ * digit planes plane[d][j, i] (uint8, K = source item i contiguous) and col_scale[j] = s_j / 256^digits
+ * (the GEMM's epilogue column scale).  Products and int32 sums are exact, so
+ * |F[u,j] - ref| <= k_u * 2^-(8*digits+1) * s_j plus one fp32 rounding.  W must be >= 0 (it is: G >= 0).
+ * scratch: 20*n bytes, 8-byte aligned.  A must be packed as uint8 (hs_pack_a_u8). */
+int hs_pack_a_u8(const int32_t* users, const int32_t* items, int64_t nnz, int64_t n_users,
+                 int64_t n_items, uint8_t* A_u8, int64_t ldk, lgc_stream_t stream);
+int hs_scale_w_u8(const float* G, int64_t ldg, int64_t n, const int32_t* ki, double lambda,
+                  float* W32, int64_t ldw, uint8_t* Wt_digits, int64_t ldk, int64_t plane_stride,
+                  int32_t digits, float* col_scale, void* scratch, lgc_stream_t stream);
 
 /* (F1) Fusion  F_new = G_score * F  (model/SpreadLightGCN/model.py:151), elementwise,
  * in place on F. */

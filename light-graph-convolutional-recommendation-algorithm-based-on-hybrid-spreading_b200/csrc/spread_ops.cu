@@ -38,6 +38,13 @@ __global__ void pack_a_kernel(const int32_t* __restrict__ users, const int32_t* 
   A[(int64_t)users[e] * ldk + items[e]] = 0x3F80;  // bf16 1.0
 }
 
+__global__ void pack_a_u8_kernel(const int32_t* __restrict__ users, const int32_t* __restrict__ items, int64_t nnz,
+                                 uint8_t* __restrict__ A, int64_t ldk) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= nnz) return;
+  A[(int64_t)users[e] * ldk + items[e]] = 1;
+}
+
 __global__ void pack_at_kernel(const int32_t* __restrict__ users, const int32_t* __restrict__ items, int64_t nnz,
                                const int32_t* __restrict__ ku, int shift, int digits, uint8_t* __restrict__ At,
                                uint8_t* __restrict__ Q, int64_t ldk, int64_t plane_stride) {
@@ -53,6 +60,12 @@ __global__ void pack_at_kernel(const int32_t* __restrict__ users, const int32_t*
   }
 }
 
+// 1/x with the reference's "zero denominator -> 1" rule.  den = a_i * b_j is zero iff a factor is zero,
+// i.e. iff item i or j has no interactions — and then G[i,j] is 0 as well, so G * inv(a) * inv(b) equals the
+// reference's G / den (up to 2 ulp of float64, far below the single fp32 rounding that follows) while the
+// per-element float64 division (the former bottleneck of this pass) becomes two multiplications.
+__device__ __forceinline__ double inv_or_one(double x) { return x == 0.0 ? 1.0 : 1.0 / x; }
+
 // W = G / (k_i^(1-l) k_j^l), 32x32 tiles, float64 arithmetic like the reference.
 __global__ void __launch_bounds__(256)
 scale_w_kernel(const float* __restrict__ G, int64_t ldg, int64_t n, const int32_t* __restrict__ ki, double lambda,
@@ -64,10 +77,10 @@ scale_w_kernel(const float* __restrict__ G, int64_t ldg, int64_t n, const int32_
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   if (threadIdx.x < 32) {
     const int64_t i = i0 + threadIdx.x;
-    sa[threadIdx.x] = i < n ? pow((double)ki[i], 1.0 - lambda) : 1.0;
+    sa[threadIdx.x] = inv_or_one(i < n ? pow((double)ki[i], 1.0 - lambda) : 1.0);
   } else if (threadIdx.x < 64) {
     const int64_t j = j0 + threadIdx.x - 32;
-    sb[threadIdx.x - 32] = j < n ? pow((double)ki[j], lambda) : 1.0;
+    sb[threadIdx.x - 32] = inv_or_one(j < n ? pow((double)ki[j], lambda) : 1.0);
   }
   __syncthreads();
 #pragma unroll
@@ -75,9 +88,7 @@ scale_w_kernel(const float* __restrict__ G, int64_t ldg, int64_t n, const int32_
     const int64_t i = i0 + r, j = j0 + tx;
     float w = 0.f;
     if (i < n && j < n) {
-      double den = sa[r] * sb[tx];
-      if (den == 0.0) den = 1.0;
-      w = (float)((double)G[i * ldg + j] / den);
+      w = (float)((double)G[i * ldg + j] * sa[r] * sb[tx]);
       if (W32) W32[i * ldw + j] = w;
     }
     tile[r][tx] = w;
@@ -95,6 +106,101 @@ scale_w_kernel(const float* __restrict__ G, int64_t ldg, int64_t n, const int32_
         Wt[p * plane_stride + j * ldk + i] = h;
         w -= __bfloat162float(h);  // exact: the residual fits in fp32
       }
+    }
+  }
+}
+
+// inv_a[i] = 1 / k_i^(1-l), inv_b[j] = 1 / k_j^l (float64, "zero -> 1"), once per lambda: keeps the slow
+// float64 pow out of the M^2 passes (it used to serialise two warps per tile while six waited).
+__global__ void scale_prep_kernel(const int32_t* __restrict__ ki, int64_t n, double lambda, double* __restrict__ inv_a,
+                                  double* __restrict__ inv_b) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double k = (double)ki[i];
+  inv_a[i] = inv_or_one(pow(k, 1.0 - lambda));
+  inv_b[i] = inv_or_one(pow(k, lambda));
+}
+
+// column maxima of W = G / (k_i^(1-l) k_j^l): cmax[j] = max_i W[i,j] (W >= 0), fp32 is enough — the
+// value only selects a power-of-two scale.  grid (n/32 column blocks, row strips of 256).
+__global__ void __launch_bounds__(256)
+colmax_w_kernel(const float* __restrict__ G, int64_t ldg, int64_t n, const double* __restrict__ inv_a,
+                const double* __restrict__ inv_b, unsigned int* __restrict__ cmax_bits) {
+  __shared__ float sa[256];
+  __shared__ float smax[8][32];
+  const int64_t j = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
+  const int64_t i0 = (int64_t)blockIdx.y * 256;
+  {
+    const int64_t i = i0 + threadIdx.x;
+    sa[threadIdx.x] = i < n ? (float)inv_a[i] : 1.f;
+  }
+  __syncthreads();
+  const int ty = threadIdx.x >> 5;
+  float m = 0.f;
+  if (j < n) {
+    const float b = (float)inv_b[j];
+    for (int r = ty; r < 256 && i0 + r < n; r += 8) m = fmaxf(m, G[(i0 + r) * ldg + j] * sa[r] * b);
+  }
+  smax[ty][threadIdx.x & 31] = m;
+  __syncthreads();
+  if (ty == 0 && j < n) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, smax[w][threadIdx.x]);
+    atomicMax(cmax_bits + j, __float_as_uint(m));  // non-negative floats order like their bit patterns
+  }
+}
+
+// W = G / (k_i^(1-l) k_j^l) quantised per column j to `digits` base-256 digits of
+// q = round(W / s_j * 256^digits), s_j = the power of two strictly above cmax[j]; digit planes are
+// written transposed (plane[d][j, i], K = source item i contiguous) for the u8 F = A.W GEMM, and
+// cs[j] = s_j / 256^digits is the epilogue column scale.  Same 32x32 tiling as scale_w_kernel.
+__global__ void __launch_bounds__(256)
+scale_w_u8_kernel(const float* __restrict__ G, int64_t ldg, int64_t n, const double* __restrict__ inv_a,
+                  const double* __restrict__ inv_b, const unsigned int* __restrict__ cmax_bits, float* __restrict__ W32, int64_t ldw,
+                  uint8_t* __restrict__ Wt, int64_t ldk, int64_t plane_stride, int digits, float* __restrict__ cs) {
+  __shared__ unsigned int tile[32][33];
+  __shared__ double sa[32], sb[32], sinv[32];
+  const double qmax = ldexp(1.0, 8 * digits) - 1.0;
+  const int64_t i0 = (int64_t)blockIdx.y * 32, j0 = (int64_t)blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (threadIdx.x < 32) {
+    const int64_t i = i0 + threadIdx.x;
+    sa[threadIdx.x] = i < n ? inv_a[i] : 1.0;
+  } else if (threadIdx.x < 64) {
+    const int t = threadIdx.x - 32;
+    const int64_t j = j0 + t;
+    sb[t] = j < n ? inv_b[j] : 1.0;
+    // s_j = 2^(e+1) with 2^e <= cmax < 2^(e+1)  (1.0 for an all-zero column); a 1 ulp head-room covers the
+    // fp32 evaluation of the maximum
+    double s = 1.0;
+    if (j < n) {
+      const float cm = __uint_as_float(cmax_bits[j]) * 1.000001f;
+      if (cm > 0.f) { int e; frexp((double)cm, &e); s = ldexp(1.0, e); }
+      if (blockIdx.y == 0 && cs) cs[j] = (float)ldexp(s, -8 * digits);
+    }
+    sinv[t] = ldexp(1.0 / s, 8 * digits);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t i = i0 + r, j = j0 + tx;
+    unsigned int qi = 0u;
+    if (i < n && j < n) {
+      const double w = (double)G[i * ldg + j] * sa[r] * sb[tx];
+      if (W32) W32[i * ldw + j] = (float)w;
+      double q = rint(w * sinv[tx]);
+      q = q < 0.0 ? 0.0 : (q > qmax ? qmax : q);
+      qi = (unsigned int)q;
+    }
+    tile[r][tx] = qi;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t j = j0 + r, i = i0 + tx;
+    if (i < n && j < n) {
+      const unsigned int qi = tile[tx][r];
+      for (int d = 0; d < digits; ++d) Wt[d * plane_stride + j * ldk + i] = (uint8_t)((qi >> (8 * d)) & 255u);
     }
   }
 }
@@ -136,6 +242,15 @@ extern "C" int hs_pack_a(const int32_t* users, const int32_t* items, int64_t nnz
   return LGC_OK;
 }
 
+extern "C" int hs_pack_a_u8(const int32_t* users, const int32_t* items, int64_t nnz, int64_t n_users,
+                            int64_t n_items, uint8_t* A_u8, int64_t ldk, lgc_stream_t stream) {
+  LGC_REQUIRE(users && items && A_u8 && nnz > 0, "pack_a_u8: null pointer / empty");
+  LGC_REQUIRE(ldk >= n_items && n_users > 0, "pack_a_u8: ldk < n_items");
+  pack_a_u8_kernel<<<(unsigned)ceil_div(nnz, 256), 256, 0, (cudaStream_t)stream>>>(users, items, nnz, A_u8, ldk);
+  LGC_LAUNCH_CHECK("pack_a_u8_kernel");
+  return LGC_OK;
+}
+
 extern "C" int hs_pack_at(const int32_t* users, const int32_t* items, int64_t nnz, int64_t n_users,
                           int64_t n_items, const int32_t* ku, int32_t shift, int32_t digits, uint8_t* At_u8,
                           uint8_t* Q_u8, int64_t ldk, int64_t plane_stride, lgc_stream_t stream) {
@@ -167,6 +282,31 @@ extern "C" int hs_scale_w(const float* G, int64_t ldg, int64_t n, const int32_t*
   scale_w_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(G, ldg, n, ki, lambda, W32, ldw,
                                                          (__nv_bfloat16*)Wt_planes, ldk, plane_stride, planes);
   LGC_LAUNCH_CHECK("scale_w_kernel");
+  return LGC_OK;
+}
+
+extern "C" int hs_scale_w_u8(const float* G, int64_t ldg, int64_t n, const int32_t* ki, double lambda, float* W32,
+                             int64_t ldw, uint8_t* Wt_digits, int64_t ldk, int64_t plane_stride, int32_t digits,
+                             float* col_scale, void* scratch, lgc_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LGC_REQUIRE(G && ki && Wt_digits && col_scale && scratch && n > 0 && ldg >= n, "scale_w_u8: bad arguments");
+  LGC_REQUIRE(((uintptr_t)scratch & 7) == 0, "scale_w_u8: scratch must be 8-byte aligned");
+  double* inv_a = (double*)scratch;          // scratch layout: n doubles, n doubles, n uint32
+  double* inv_b = inv_a + n;
+  uint32_t* colmax_scratch = (uint32_t*)(inv_b + n);
+  LGC_REQUIRE(digits >= 1 && digits <= 4 && ldk >= n, "scale_w_u8: digits in 1..4, ldk >= n");
+  LGC_REQUIRE(digits == 1 || plane_stride >= n * ldk, "scale_w_u8: plane stride overlaps planes");
+  LGC_REQUIRE(!W32 || ldw >= n, "scale_w_u8: ldw < n");
+  LGC_CUDA(cudaMemsetAsync(colmax_scratch, 0, sizeof(uint32_t) * (size_t)n, stream));
+  scale_prep_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(ki, n, lambda, inv_a, inv_b);
+  LGC_LAUNCH_CHECK("scale_prep_kernel");
+  dim3 g1((unsigned)ceil_div(n, 32), (unsigned)ceil_div(n, 256));
+  colmax_w_kernel<<<g1, 256, 0, stream>>>(G, ldg, n, inv_a, inv_b, colmax_scratch);
+  LGC_LAUNCH_CHECK("colmax_w_kernel");
+  dim3 g2((unsigned)ceil_div(n, 32), (unsigned)ceil_div(n, 32));
+  scale_w_u8_kernel<<<g2, 256, 0, stream>>>(G, ldg, n, inv_a, inv_b, colmax_scratch, W32, ldw, Wt_digits, ldk,
+                                           plane_stride, digits, col_scale);
+  LGC_LAUNCH_CHECK("scale_w_u8_kernel");
   return LGC_OK;
 }
 

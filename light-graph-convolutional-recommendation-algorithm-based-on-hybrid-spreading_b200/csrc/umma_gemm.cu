@@ -547,7 +547,7 @@ static int check_gemm_args(int kind, const void* A, int64_t lda, const void* B, 
   LGC_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem");
   LGC_REQUIRE(lda >= K && ldb >= K && ldc >= N, "gemm: leading dimension smaller than extent");
   if (kind == 0) LGC_REQUIRE(planes >= 1 && planes <= 3, "gemm: bf16 kind takes 1..3 planes");
-  else LGC_REQUIRE(planes == 1 || planes == 2 || planes == 4, "gemm: u8 kind takes 1, 2 or 4 planes");
+  else LGC_REQUIRE(planes >= 1 && planes <= 4, "gemm: u8 kind takes 1..4 planes");
   LGC_REQUIRE(planes == 1 || plane_stride >= N * ldb, "gemm: plane stride overlaps planes");
   return LGC_OK;
 }
@@ -638,7 +638,7 @@ extern "C" int hs_gemm_planes(int32_t kind, const void* A, int64_t lda, const vo
     umma_gemm_pair_kernel<KD, PL><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmBh, p);                   \
   }
     LGC_GEMM_PAIR_CASE(0, 1) LGC_GEMM_PAIR_CASE(0, 2) LGC_GEMM_PAIR_CASE(0, 3)
-    LGC_GEMM_PAIR_CASE(1, 1) LGC_GEMM_PAIR_CASE(1, 2) LGC_GEMM_PAIR_CASE(1, 4)
+    LGC_GEMM_PAIR_CASE(1, 1) LGC_GEMM_PAIR_CASE(1, 2) LGC_GEMM_PAIR_CASE(1, 3) LGC_GEMM_PAIR_CASE(1, 4)
 #undef LGC_GEMM_PAIR_CASE
     LGC_LAUNCH_CHECK("umma_gemm_pair_kernel");
     return LGC_OK;
@@ -657,7 +657,7 @@ extern "C" int hs_gemm_planes(int32_t kind, const void* A, int64_t lda, const vo
     umma_gemm_kernel<KD, PL><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, p);                        \
   }
   LGC_GEMM_CASE(0, 1) LGC_GEMM_CASE(0, 2) LGC_GEMM_CASE(0, 3)
-  LGC_GEMM_CASE(1, 1) LGC_GEMM_CASE(1, 2) LGC_GEMM_CASE(1, 4)
+  LGC_GEMM_CASE(1, 1) LGC_GEMM_CASE(1, 2) LGC_GEMM_CASE(1, 3) LGC_GEMM_CASE(1, 4)
 #undef LGC_GEMM_CASE
   LGC_LAUNCH_CHECK("umma_gemm_kernel");
   return LGC_OK;

@@ -48,6 +48,8 @@ _SIGS = {
     "hs_gemm_config": (C.c_int, [_i32]),
     "hs_gemm_use_cta_pair": (C.c_int, [_i32]),
     "hs_scale_w": (C.c_int, [_p, _i64, _i64, _p, _f64, _p, _i64, _p, _i64, _i64, _i32, _p]),
+    "hs_pack_a_u8": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _i64, _p]),
+    "hs_scale_w_u8": (C.c_int, [_p, _i64, _i64, _p, _f64, _p, _i64, _p, _i64, _i64, _i32, _p, _p, _p]),
     "hs_hadamard": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _p]),
     "lgc_ipc_get_handle": (C.c_int, [_p, _p]),
     "lgc_ipc_open_handle": (C.c_int, [_p, C.POINTER(_p)]),

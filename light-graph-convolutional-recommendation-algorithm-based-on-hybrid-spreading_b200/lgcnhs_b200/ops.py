@@ -303,15 +303,24 @@ class SpreadingEngine:
     with G cached across lambda values (the findLambda.py:81-116 pattern).
     """
 
+    W_MODES = {"u8x4": (1, 4), "u8x3": (1, 3), "bf16x3": (0, 3), "bf16x2": (0, 2)}
+
     def __init__(self, n_users: int, n_items: int, users: torch.Tensor, items: torch.Tensor,
-                 w_planes: int = 3, g_kind: str = "u8"):
+                 w_mode: str = "u8x4", g_kind: str = "u8"):
+        """w_mode selects how the real operand W of F = A.W reaches the tensor cores:
+        "u8x4"/"u8x3": per-column fixed point, 4/3 base-256 digit planes, exact int32 accumulation
+                       (|err| <= k_u 2^-(8d+1) s_j; 2 / 1.5 bf16-pass equivalents);
+        "bf16x3"/"bf16x2": hi/mid(/lo) bf16 split, fp32 accumulation drained every 8 K-blocks."""
         users = _req(users.to(torch.int32).contiguous(), torch.int32, "users")
         items = _req(items.to(torch.int32).contiguous(), torch.int32, "items")
+        if w_mode not in self.W_MODES:
+            raise LgcnhsError(f"w_mode must be one of {sorted(self.W_MODES)}")
         self.U, self.M = int(n_users), int(n_items)
         self.dev = users.device
         self.users, self.items = users, items
         self.nnz = int(users.numel())
-        self.w_planes = int(w_planes)
+        self.w_mode = w_mode
+        self.w_kind, self.w_planes = self.W_MODES[w_mode]
         self.g_kind = g_kind
         L = lib()
         U, M, dev = self.U, self.M, self.dev
@@ -322,12 +331,19 @@ class SpreadingEngine:
                            _stream()), "degrees")
         # the deduplicated bit-packed A doubles as the top-k exclusion mask (train ⊕ val items)
         self.excl = ExclusionMask(bitmap, U, M, M)
-        self.ldM = _pad(M, 64)   # K extent (items) of A and W^T planes, bf16
-        self.A = torch.zeros((U, self.ldM), dtype=torch.bfloat16, device=dev)
-        check(L.hs_pack_a(_ptr(users), _ptr(items), self.nnz, U, M, _ptr(self.A), self.ldM, _stream()), "pack_a")
+        # K extent (items) of A and the W^T planes: one 128-byte swizzle atom per K-block
+        self.ldM = _pad(M, 128 if self.w_kind == 1 else 64)
+        if self.w_kind == 1:
+            self.A = torch.zeros((U, self.ldM), dtype=torch.uint8, device=dev)
+            check(L.hs_pack_a_u8(_ptr(users), _ptr(items), self.nnz, U, M, _ptr(self.A), self.ldM, _stream()), "pack_a_u8")
+            self.col_scale = torch.empty(M, dtype=torch.float32, device=dev)
+            self._scratch = torch.empty(20 * M, dtype=torch.uint8, device=dev)
+        else:
+            self.A = torch.zeros((U, self.ldM), dtype=torch.bfloat16, device=dev)
+            check(L.hs_pack_a(_ptr(users), _ptr(items), self.nnz, U, M, _ptr(self.A), self.ldM, _stream()), "pack_a")
+            self.col_scale = None
         self.G: Optional[torch.Tensor] = None
         self.Wt: Optional[torch.Tensor] = None
-
 
     def excl_items(self, u: int) -> torch.Tensor:
         """Deduplicated item ids of user u (row u of A), ascending — decoded from the bit-packed mask."""
@@ -367,16 +383,22 @@ class SpreadingEngine:
         return G
 
     def scale(self, lam: float, G: Optional[torch.Tensor] = None, want_w32: bool = False):
-        """W = HybridS(A, G, lambda) (model/SpreadMethod/model.py:63-85) -> bf16 planes of W^T (+ fp32 W)."""
+        """W = HybridS(A, G, lambda) (model/SpreadMethod/model.py:63-85) -> operand planes of W^T (+ fp32 W)."""
         G = self.G if G is None else G
         if G is None:
             raise LgcnhsError("scale(): general_w() has not been computed")
         M, dev = self.M, self.dev
         if self.Wt is None:
-            self.Wt = torch.zeros((self.w_planes, M, self.ldM), dtype=torch.bfloat16, device=dev)
+            dt = torch.uint8 if self.w_kind == 1 else torch.bfloat16
+            self.Wt = torch.zeros((self.w_planes, M, self.ldM), dtype=dt, device=dev)
         W32 = torch.empty((M, M), dtype=torch.float32, device=dev) if want_w32 else None
-        check(lib().hs_scale_w(_ptr(G), int(G.stride(0)), M, _ptr(self.ki), float(lam), _ptr(W32), M, _ptr(self.Wt),
-                               self.ldM, M * self.ldM, self.w_planes, _stream()), "scale_w")
+        if self.w_kind == 1:
+            check(lib().hs_scale_w_u8(_ptr(G), int(G.stride(0)), M, _ptr(self.ki), float(lam), _ptr(W32), M,
+                                      _ptr(self.Wt), self.ldM, M * self.ldM, self.w_planes, _ptr(self.col_scale),
+                                      _ptr(self._scratch), _stream()), "scale_w_u8")
+        else:
+            check(lib().hs_scale_w(_ptr(G), int(G.stride(0)), M, _ptr(self.ki), float(lam), _ptr(W32), M, _ptr(self.Wt),
+                                   self.ldM, M * self.ldM, self.w_planes, _stream()), "scale_w")
         return W32
 
     def resource(self, user_range: Optional[tuple[int, int]] = None, out: Optional[torch.Tensor] = None):
@@ -384,7 +406,7 @@ class SpreadingEngine:
         if self.Wt is None:
             raise LgcnhsError("resource(): scale() has not been called")
         u0, u1 = (0, self.U) if user_range is None else user_range
-        return gemm_planes(0, self.A[u0:u1], self.Wt, u1 - u0, self.M, self.M, out=out)
+        return gemm_planes(self.w_kind, self.A[u0:u1], self.Wt, u1 - u0, self.M, self.M, out=out, cs=self.col_scale)
 
     def recommend(self, lam: float, k: int, filtered: bool = True, gscore: Optional[torch.Tensor] = None,
                   user_range: Optional[tuple[int, int]] = None, F_out: Optional[torch.Tensor] = None):

@@ -77,10 +77,13 @@ def getResource(A: np.ndarray, W: np.ndarray) -> np.ndarray:
     eng = _engine_from_dense(A)
     M = eng.M
     Wd = torch.from_numpy(np.ascontiguousarray(W, dtype=np.float32)).to(eng.dev)
-    if eng.Wt is None:
-        eng.Wt = torch.zeros((eng.w_planes, M, eng.ldM), dtype=torch.bfloat16, device=eng.dev)
-    # identity scaling (lambda = 0 with unit degrees) just transposes + splits W into the operand planes
-    ones = torch.ones(M, dtype=torch.int32, device=eng.dev)
-    check(lib().hs_scale_w(Wd.data_ptr(), M, M, ones.data_ptr(), 0.0, 0, M, eng.Wt.data_ptr(), eng.ldM, M * eng.ldM,
-                           eng.w_planes, torch.cuda.current_stream().cuda_stream), "split W")
+    if float(Wd.min()) < 0.0:
+        raise ValueError("getResource: W must be non-negative (transfer weights are), got negative entries")
+    # identity scaling (unit degrees) re-uses the fused scale kernel to transpose W and emit the operand planes
+    ki = eng.ki
+    eng.ki = torch.ones(M, dtype=torch.int32, device=eng.dev)
+    try:
+        eng.scale(0.0, G=Wd)
+    finally:
+        eng.ki = ki
     return eng.resource().double().cpu().numpy()

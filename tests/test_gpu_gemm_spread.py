@@ -61,8 +61,9 @@ def test_gemm_u8_digits_exact(dev, M, N, K, planes):
     assert torch.equal(C.cpu(), ref)
 
 
+@pytest.mark.parametrize("w_mode", ["u8x4", "u8x3", "bf16x3", "bf16x2"])
 @pytest.mark.parametrize("name,lam", [("tiny", 0.3), ("small", 0.0), ("small", 1.0), ("ml-100k", 0.3), ("ml-100k", 0.85)])
-def test_spreading_pipeline(dev, name, lam):
+def test_spreading_pipeline(dev, name, lam, w_mode):
     """G, W, F and the filtered top-k against the float64 reference restatement."""
     from lgcnhs_b200 import ops
     from lgcnhs_b200.synth import synth_shape
@@ -75,7 +76,8 @@ def test_spreading_pipeline(dev, name, lam):
     G = S.get_spreading_general_mat(A)
     W = S.hybrids(A, G, lam)
     F = S.get_resource(A, W)
-    eng = ops.SpreadingEngine(d.n_users, d.n_items, torch.from_numpy(users).to(dev), torch.from_numpy(items).to(dev))
+    eng = ops.SpreadingEngine(d.n_users, d.n_items, torch.from_numpy(users).to(dev), torch.from_numpy(items).to(dev),
+                              w_mode=w_mode)
     assert np.array_equal(eng.ku.cpu().numpy(), A.sum(1).astype(np.int32))
     assert np.array_equal(eng.ki.cpu().numpy(), A.sum(0).astype(np.int32))
     Gd = eng.general_w()
