@@ -186,7 +186,7 @@ def run_reference(args):
                                    "scatter_add, PyG-equivalent oracle port), algorithmic bytes of 1 layer / time"},
         "e2e": {"value": round(gbs, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -292,7 +292,27 @@ def training_leg(dev, steps: int, warmup: int):
             "eval_what": "layer-0 score (fp32 FMA) + train-pair fill(-1024) + top-20 over all 91 599 items, block-wise"}
 
 
+_REAL_STDOUT = None
+
+
+def _capture_stdout():
+    """The contract is ONE JSON line on stdout; libraries (NCCL's version banner, torchrun notices) also
+    write to fd 1.  Point fd 1 at stderr for the whole run and keep the real stdout for the JSON line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _capture_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -459,7 +479,7 @@ def main():
                                 "sample": "1 of 3 propagation layers over the full graph (PyG-equivalent oracle port: "
                                           "gcn_norm + index_select + scatter_add); %.2f s per layer" % sec}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
