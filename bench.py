@@ -203,14 +203,20 @@ def spreading_leg(dev, steps: int, warmup: int):
     items = torch.from_numpy(d.items[sel]).to(dev)
     eng = ops.SpreadingEngine(d.n_users, d.n_items, users, items)
     U, M = d.n_users, d.n_items
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
-    # G build (int8 tcgen05 GEMM), timed alone
-    eng.general_w()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
+    # G build: operand packing (memset + scatter of A^T and the digit planes) and the int8 tcgen05 GEMM, timed apart
+    ops_g = eng.pack_g_operands()
+    G = eng.general_w(operands=ops_g)
     torch.cuda.synchronize()
     ev[0].record()
     for _ in range(steps):
-        eng.general_w()
+        eng.general_w(operands=ops_g, out=G)
     ev[1].record()
+    ev[6].record()
+    for _ in range(steps):
+        ops_p = eng.pack_g_operands()
+    ev[7].record()
+    del ops_p
     F = torch.empty((U, (M + 3) // 4 * 4), dtype=torch.float32, device=dev)[:, :M]
     lams = np.linspace(0.0, 1.0, steps + warmup)
     for lam in lams[:warmup]:
@@ -227,13 +233,16 @@ def spreading_leg(dev, steps: int, warmup: int):
     ev[5].record()
     torch.cuda.synchronize()
     t_g = ev[0].elapsed_time(ev[1]) / steps * 1e-3
+    t_pack = ev[6].elapsed_time(ev[7]) / steps * 1e-3
     t_step = ev[2].elapsed_time(ev[3]) / steps * 1e-3
     t_f = ev[4].elapsed_time(ev[5]) / steps * 1e-3
     _, peak_burst, _, how = peaks()
     flops = 2.0 * M * M * U
     return {
         "workload": f"hybrid spreading ml-1m shape ({U}x{M}, nnz(A)={sel.size}), top-20 full-rank filtered",
-        "g_build": {"ms": round(t_g * 1e3, 4), "tflops": round(flops / t_g / 1e12, 2), "kind": "u8 x4 digits, exact"},
+        "g_gemm": {"ms": round(t_g * 1e3, 4), "tflops": round(flops / t_g / 1e12, 2),
+                   "kind": "G = A^T K_u^-1 A, u8 x4 digit planes of round(2^s/k_u), exact int32 accumulate",
+                   "operand_pack_ms": round(t_pack * 1e3, 4)},
         "f_gemm": {"ms": round(t_f * 1e3, 4), "tflops": round(flops / t_f / 1e12, 2),
                    "kind": "u8 x4 digit planes of per-column fixed-point W, exact int32 accumulate (w_mode u8x4)"},
         "lambda_step": {"ms": round(t_step * 1e3, 4), "users_per_s": round(U / t_step, 1),
@@ -289,7 +298,7 @@ def training_leg(dev, steps: int, warmup: int):
             "step_algorithmic_gbs": round(gbs, 1), "step_frac_of_hbm_peak": round(gbs / hbm, 3),
             "what": "2K fused SpMM layers (fwd + grad) + fused BPR fwd/bwd scatter + 2 Adam kernels, no host sync",
             "eval_ms": round(ms_eval, 2), "eval_users_per_s": round(d.n_users / (ms_eval * 1e-3), 1),
-            "eval_what": "layer-0 score (fp32 FMA) + train-pair fill(-1024) + top-20 over all 91 599 items, block-wise"}
+            "eval_what": "ONE fused kernel: layer-0 score tiles (fp32 FMA) + train-pair fill(-1024) + top-20 over all 91 599 items; the U x M score matrix is never written"}
 
 
 _REAL_STDOUT = None

@@ -166,6 +166,22 @@ int lgc_score_block(const float* Xu, const float* Xi, int64_t u0, int64_t u1,
 int lgc_topk_rows(const float* S, int64_t n_rows, int64_t n_cols, int64_t lds,
                   const uint32_t* excl_mask, int64_t mask_stride_bits, int64_t row_offset,
                   int32_t k, int64_t* out_idx, float* out_val, lgc_stream_t stream);
+/* ------------------------------------------------------------------------------------
+ * (P8 / F1) FUSED score + seen-pair rule + top-k: the (U, M) score matrix is never written.
+ * One call replaces torch.matmul(user_embedding, item_embedding.T), score[users, items] = -1024
+ * and torch.topk(score, k) of model/LightGCN/recommend.py:86-114 (== evaluation.py:34-52), and,
+ * with `mul`, the G_score * F Hadamard product + argsort/filter loop of
+ * model/SpreadLightGCN/model.py:151 + recommend.py:34-46 (== SpreadLightGCNOpti).
+ *   value(u, i) = (seen(u,i) ? fill : <Xu[u], Xi[i]>) * (mul ? mul[(u-u0)*ldmul + i] : 1)
+ *   seen_ptr/seen_idx: CSR over ALL users of seen item ids, ascending per row (may be null).
+ *   exclude_seen != 0: seen items are dropped from the ranking instead of taking `fill`.
+ *   out_idx int64 (u1-u0, k), out_val fp32 (u1-u0, k) or null; sorted by value descending,
+ *   ties -> larger index first.  k <= 128, k <= n_items, dim in {32, 64}.
+ * ---------------------------------------------------------------------------------- */
+int lgc_score_topk(const float* Xu, const float* Xi, int64_t u0, int64_t u1, int64_t n_items,
+                   int32_t dim, const int32_t* seen_ptr, const int32_t* seen_idx, float fill,
+                   int32_t exclude_seen, const float* mul, int64_t ldmul, int32_t k,
+                   int64_t* out_idx, float* out_val, lgc_stream_t stream);
 /* CSR (rowptr, column ids) -> bit-packed mask with the given row stride; mask zero-filled by
  * the caller, (n_rows * stride_bits + 31) / 32 words. */
 int lgc_mask_from_csr(const int32_t* ptr, const int32_t* idx, int64_t n_rows, int64_t n_cols,

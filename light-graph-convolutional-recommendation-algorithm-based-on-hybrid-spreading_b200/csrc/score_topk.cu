@@ -10,6 +10,7 @@
 //       (/root/reference/model/SpreadMethod/recommend.py:35-47, 32.8 ms/user measured), as one
 //       radix-select pass structure per row: exact, deterministic, ties -> larger index first.
 #include "common.cuh"
+#include "select.cuh"
 
 namespace lgc {
 
@@ -81,107 +82,372 @@ __global__ void seen_fill_kernel(const int32_t* __restrict__ seen_ptr, const int
 }
 
 // ------------------------------------------------------------------------------------------
-// row-wise masked top-k on the 64-bit composite key (ordered fp32 value, column index)
+// row-wise masked top-k: ONE WARP per row, threshold + candidate buffer (select.cuh)
 // ------------------------------------------------------------------------------------------
-// ONE WARP per row, k <= 128 << n_cols, no shared memory and no barriers.  Each lane streams its
-// strided share of the row once (coalesced 128 B per warp load, evict-first, 8 loads in flight)
-// and keeps a sorted list of its LIST largest (value key, column) pairs.  The hot loop is one
-// 32-bit compare per element: only values that beat the lane's current LIST-th best go on to the
-// exclusion test (one bit of the bit-packed rows x n_cols mask) and the insertion.  Then k rounds
-// of a warp-wide arg-max over the list heads — two REDUX instructions (value, then column among
-// the equal values) — pop the winners in final order.  A lane whose list runs dry re-streams its
-// share below its last popped pair, so the result is exact for any distribution.  (value, column)
-// pairs are unique, so the result is deterministic and equal values rank the LARGER column first
-// (np.argsort(row)[::-1] order).  If fewer than k columns are selectable the tail is -1.
+// Each lane streams its share of the row once (128-bit loads, 4 in flight per lane, evict-first)
+// and the hot loop is one 32-bit compare per value against the row's current k-th best.  The few
+// survivors (~k ln(n/k) per row) go through the exclusion test (one bit of the bit-packed
+// rows x n_cols mask), are appended to the warp's shared-memory buffer with a ballot/prefix, and
+// the buffer is compacted by an in-register bitonic sort when it fills.  Exact for any
+// distribution; deterministic; equal values rank the LARGER column first.  If fewer than k
+// columns are selectable the tail is (-1, -inf).
 constexpr int kTopkWarps = 8;
 constexpr int kTopkMaxK = 128;
-constexpr int kTopkUnroll = 8;
 
-__device__ __forceinline__ uint32_t float_key(float x) {
-  const uint32_t b = __float_as_uint(x);
-  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);  // monotone: larger float -> larger key
-}
-__device__ __forceinline__ float key_float(uint32_t k) {
-  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
-}
-
-template <int LIST>
+template <int CAP, bool VEC>
 __global__ void __launch_bounds__(kTopkWarps * 32)
 topk_rows_kernel(const float* __restrict__ S, int n_rows, int n, int64_t lds, const uint32_t* __restrict__ mask,
                  int64_t mask_stride_bits, int64_t row_offset, int k, int64_t* __restrict__ out_idx,
                  float* __restrict__ out_val) {
+  constexpr int E = CAP / 32;
+  __shared__ unsigned long long s_buf[kTopkWarps][CAP];
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * kTopkWarps + (threadIdx.x >> 5);
   if (r >= n_rows) return;
+  unsigned long long* buf = s_buf[threadIdx.x >> 5];
   const float* row = S + r * lds;
   const int64_t bit0 = (row_offset + r) * mask_stride_bits;
   const uint32_t* mrow = mask ? mask + (bit0 >> 5) : nullptr;
   const uint32_t boff = (uint32_t)(bit0 & 31);
+  const uint32_t lt_mask = (1u << lane) - 1u;
 
-  uint32_t lv[LIST], lc[LIST];  // value keys / column+1, sorted descending; lc == 0 marks an empty slot
-  // keep the LIST largest pairs strictly below (bv, bc) among this lane's columns (ascending column order,
-  // so among equal values the later column is the larger pair)
-  auto stream = [&](uint32_t bv, uint32_t bc) {
-#pragma unroll
-    for (int i = 0; i < LIST; ++i) { lv[i] = 0u; lc[i] = 0u; }
-    for (int c0 = lane; c0 < n; c0 += 32 * kTopkUnroll) {
-      float v[kTopkUnroll];
-#pragma unroll
-      for (int u = 0; u < kTopkUnroll; ++u) {
-        const int c = c0 + 32 * u;
-        v[u] = c < n ? __ldcs(row + c) : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < kTopkUnroll; ++u) {
-        const int c = c0 + 32 * u;
-        const uint32_t vk = float_key(v[u]);
-        // fast reject: not better than this lane's LIST-th best (an empty slot has lv == 0)
-        if (c < n && (vk >= lv[LIST - 1] || lc[LIST - 1] == 0u)) {
-          const bool below = vk < bv || (vk == bv && (uint32_t)(c + 1) < bc);
+  int cnt = 0;
+  unsigned long long thr = 0ull;
+  uint32_t thr_hi = 0u;
+
+  // warp-collective: every lane offers one (value key, column) pair; `live` = column in range
+  auto offer = [&](uint32_t vk, int c, bool live) {
+    const unsigned long long key = make_key(vk, (uint32_t)c);
+    bool pass = live && key > thr;
+    if (pass && mrow) {
+      const uint32_t b = boff + (uint32_t)c;
+      pass = !((__ldg(mrow + (b >> 5)) >> (b & 31)) & 1u);
+    }
+    uint32_t m = __ballot_sync(0xffffffffu, pass);
+    if (m == 0u) return;
+    if (cnt + __popc(m) > CAP) {
+      cnt = warp_compact<E>(buf, cnt, k, lane, &thr);
+      thr_hi = (uint32_t)(thr >> 32);
+      pass = pass && key > thr;
+      m = __ballot_sync(0xffffffffu, pass);
+    }
+    if (pass) buf[cnt + __popc(m & lt_mask)] = key;
+    cnt += __popc(m);
+  };
+
+  // Threshold seed (k <= 32): every lane takes the best selectable pair among its first values; the k-th largest
+  // of the 32 lane maxima is a valid lower bound of the row's k-th best (they are 32 distinct selectable
+  // elements), so the first iterations append a few dozen candidates instead of all of them.
+  if (CAP == 64) {
+    unsigned long long best[1] = {0ull};
+    constexpr int SEED = VEC ? 16 : 8;
+#pragma unroll 1
+    for (int q = 0; q < SEED; ++q) {
+      const int c = VEC ? (q >> 2) * 128 + lane * 4 + (q & 3) : q * 32 + lane;
+      if (c < n) {
+        const unsigned long long key = make_key(float_key(__ldg(row + c)), (uint32_t)c);
+        if (key > best[0]) {
           bool ex = false;
           if (mrow) {
             const uint32_t b = boff + (uint32_t)c;
             ex = (__ldg(mrow + (b >> 5)) >> (b & 31)) & 1u;
           }
-          if (below && !ex) {
-            lv[LIST - 1] = vk;
-            lc[LIST - 1] = (uint32_t)(c + 1);
-            bool moving = true;  // bubble the new pair up; it stops at the first strictly larger value
+          if (!ex) best[0] = key;
+        }
+      }
+    }
+    warp_sort_desc<1>(best, lane);
+    const unsigned long long seed = __shfl_sync(0xffffffffu, best[0], k - 1);
+    if (seed != 0ull) {
+      thr = seed - 1ull;  // the seed element itself must still pass
+      thr_hi = (uint32_t)(thr >> 32);
+    }
+  }
+
+  // One iteration = NV values per lane.  Fast path: one 32-bit compare per value builds the lane's pass bitmask;
+  // slow path (a single, non-unrolled call site, so the sort network is instantiated once): rounds in which every
+  // lane offers its next surviving value.
+  constexpr int NV = VEC ? 16 : 8;
+  constexpr int COLS = 32 * NV;
+  for (int c0 = 0; c0 < n; c0 += COLS) {
+    uint32_t vk[NV];  // indexed dynamically in the slow path -> lives in local memory (L1), the fast path stays in registers
+    uint32_t bits = 0u;
+    if (VEC) {
+      float4 v[4];
 #pragma unroll
-            for (int i = LIST - 1; i > 0; --i) {
-              moving = moving && (lc[i - 1] == 0u || lv[i] >= lv[i - 1]);
-              if (moving) {
-                const uint32_t tv = lv[i], tc = lc[i];
-                lv[i] = lv[i - 1]; lc[i] = lc[i - 1];
-                lv[i - 1] = tv; lc[i - 1] = tc;
-              }
-            }
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + u * 128 + lane * 4;
+        v[u] = c < n ? __ldcs(reinterpret_cast<const float4*>(row + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float f[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t x = float_key(f[q]);
+          vk[u * 4 + q] = x;
+          if (c0 + u * 128 + lane * 4 + q < n && x >= thr_hi) bits |= 1u << (u * 4 + q);
+        }
+      }
+    } else {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int c = c0 + u * 32 + lane;
+        v[u] = c < n ? __ldcs(row + c) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const uint32_t x = float_key(v[u]);
+        vk[u] = x;
+        if (c0 + u * 32 + lane < n && x >= thr_hi) bits |= 1u << u;
+      }
+    }
+#pragma unroll 1
+    while (__any_sync(0xffffffffu, bits != 0u)) {
+      const bool has = bits != 0u;
+      const int q = has ? __ffs(bits) - 1 : 0;
+      bits &= bits - 1u;
+      const int c = VEC ? c0 + (q >> 2) * 128 + lane * 4 + (q & 3) : c0 + q * 32 + lane;
+      offer(vk[q], c, has);
+    }
+  }
+
+  cnt = warp_compact<E>(buf, cnt, k, lane, &thr);
+  for (int i = lane; i < k; i += 32) {
+    const unsigned long long key = buf[i];
+    out_idx[r * k + i] = i < cnt ? (int64_t)(uint32_t)(key & 0xffffffffull) : -1;
+    if (out_val) out_val[r * k + i] = i < cnt ? key_float((uint32_t)(key >> 32)) : -INFINITY;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fused score + seen-pair rule + top-k: the (U, M) score matrix never exists
+// ------------------------------------------------------------------------------------------
+// One CTA owns 64 users and walks over ALL items in tiles of 128: the tile's item embeddings are
+// staged (transposed) in shared memory while the next tile's rows are already in flight in
+// registers; 256 threads hold a 4 x 8 register tile of fp32-FMA dot products each.  A score that
+// beats its row's current k-th best is appended to that row's candidate buffer in shared memory
+// (select.cuh); full buffers are compacted by one warp each.  Seen pairs (CSR, binary search, only
+// evaluated for the few survivors) either take the fill value (-1024: the reference's
+// score[users, items] = -1024 followed by torch.topk) or are dropped (the filtered lists of the
+// spreading family); an optional multiplier matrix fuses the Hadamard product F_new = G * F of
+// /root/reference/model/SpreadLightGCN/model.py:151 into the same pass.
+constexpr int kFTI = 128, kFThreads = 256;
+
+// d = a * b + c on two packed fp32 lanes (Blackwell FFMA2): each half is an IEEE round-to-nearest fmaf, so the
+// result is bit-identical to the scalar loop of lgc_score_block at half the FMA-pipe issue slots (a scalar
+// FFMA issues every second cycle per scheduler on sm_100: the kernel measured 26 TFLOP/s with them).
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long dup2(float a) {  // (a, a)
+  unsigned long long d;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(d) : "f"(a));
+  return d;
+}
+
+template <int DIM, int TU, int CAP>
+constexpr size_t score_topk_smem() {
+  return (size_t)DIM * (TU + 4) * 4 + 2 * (size_t)DIM * (kFTI + 4) * 4 + (size_t)TU * CAP * 8 + TU * 8 + TU * 4 + TU * 4;
+}
+
+__device__ __forceinline__ bool csr_contains(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                                             int64_t row, int32_t col) {
+  int lo = __ldg(ptr + row), hi = __ldg(ptr + row + 1);
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const int32_t v = __ldg(idx + mid);
+    if (v == col) return true;
+    if (v < col) lo = mid + 1; else hi = mid;
+  }
+  return false;
+}
+
+// TU users per CTA (64 or 128): a thread owns TU/16 users x 8 items.  The loop is bound by the bytes shared
+// memory returns to registers per FMA, so the larger tile (8 x 8: 64 B per 64 FMAs) is used whenever the
+// candidate buffers of 128 rows fit next to the double-buffered item tile (k <= 32).
+template <int DIM, int TU, int CAP, bool MUL>
+__global__ void __launch_bounds__(kFThreads, ((TU == 64 && CAP <= 64) ? 2 : 1))
+score_topk_kernel(const float* __restrict__ Xu, const float* __restrict__ Xi, int64_t u0, int64_t u1, int n_items,
+                  const int32_t* __restrict__ seen_ptr, const int32_t* __restrict__ seen_idx, float fill,
+                  int exclude_seen, const float* __restrict__ mul, int64_t ldmul, int k,
+                  int64_t* __restrict__ out_idx, float* __restrict__ out_val) {
+  constexpr int E = CAP / 32;
+  constexpr int UT = TU / 16;                       // users per thread
+  constexpr int CH = DIM / 4;                       // float4 chunks per embedding row
+  constexpr int LDI = (kFTI * CH) / kFThreads;      // item-tile float4 loads per thread
+  constexpr int NS = UT * 8;                        // scores per thread and tile
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float (*sU)[TU + 4] = reinterpret_cast<float (*)[TU + 4]>(smem_raw);
+  // the item tile is double-buffered: tile t+1 is staged while tile t is still being read, one barrier per tile
+  float (*sI0)[kFTI + 4] = reinterpret_cast<float (*)[kFTI + 4]>(smem_raw + (size_t)DIM * (TU + 4) * 4);
+  unsigned long long* cand =
+      reinterpret_cast<unsigned long long*>(smem_raw + (size_t)DIM * (TU + 4) * 4 + 2 * (size_t)DIM * (kFTI + 4) * 4);
+  unsigned long long* thr = cand + (size_t)TU * CAP;
+  int* cnt = reinterpret_cast<int*>(thr + TU);
+  int* res = cnt + TU;  // entries [0, res) of a row's buffer already went through the seen-pair rule
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int64_t ub = u0 + (int64_t)blockIdx.x * TU;
+
+  if (tid < TU) { thr[tid] = 0ull; cnt[tid] = 0; res[tid] = 0; }
+  for (int f = tid; f < TU * CH; f += kFThreads) {
+    const int r = f % TU, c = f / TU;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ub + r < u1) a = __ldg(reinterpret_cast<const float4*>(Xu + (ub + r) * DIM + c * 4));
+    sU[c * 4 + 0][r] = a.x; sU[c * 4 + 1][r] = a.y; sU[c * 4 + 2][r] = a.z; sU[c * 4 + 3][r] = a.w;
+  }
+
+  float4 pre[LDI];
+  auto fetch = [&](int ib) {
+#pragma unroll
+    for (int m = 0; m < LDI; ++m) {
+      const int f = tid + kFThreads * m, r = f % kFTI, c = f / kFTI;
+      pre[m] = ib + r < n_items ? __ldg(reinterpret_cast<const float4*>(Xi + (int64_t)(ib + r) * DIM + c * 4))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto stage = [&](int buf) {
+    float (*sI)[kFTI + 4] = sI0 + buf * DIM;
+#pragma unroll
+    for (int m = 0; m < LDI; ++m) {
+      const int f = tid + kFThreads * m, r = f % kFTI, c = f / kFTI;
+      sI[c * 4 + 0][r] = pre[m].x; sI[c * 4 + 1][r] = pre[m].y; sI[c * 4 + 2][r] = pre[m].z; sI[c * 4 + 3][r] = pre[m].w;
+    }
+  };
+  fetch(0);
+  stage(0);
+  if (kFTI < n_items) fetch(kFTI);
+  __syncthreads();
+
+  // One warp: apply the seen-pair rule to the not yet resolved entries of a row's buffer (the binary searches of
+  // the lanes overlap; candidates are appended unchecked so that no global-memory latency sits between the tiles'
+  // barriers), then keep the k best and raise the row's threshold.
+  auto compact_row = [&](int row, int n) {
+    unsigned long long* base = cand + (size_t)row * CAP;
+    if (seen_ptr) {
+      const int r0 = res[row];
+#pragma unroll 1
+      for (int idx = r0 + lane; idx < n; idx += 32) {
+        const unsigned long long key = base[idx];
+        const int32_t item = (int32_t)(uint32_t)(key & 0xffffffffull);
+        if (csr_contains(seen_ptr, seen_idx, ub + row, item)) {
+          float v = fill;
+          if (MUL) v *= __ldg(mul + (ub + row - u0) * ldmul + item);
+          base[idx] = exclude_seen ? 0ull : make_key(float_key(v), (uint32_t)item);
+        }
+      }
+    }
+    unsigned long long t;
+    const int kept = warp_compact<E>(base, n, k, lane, &t);
+    if (lane == 0) { cnt[row] = kept; thr[row] = t; res[row] = kept; }
+    __syncwarp();
+    return kept;
+  };
+
+  int buf = 0;
+  for (int ib = 0; ib < n_items; ib += kFTI, buf ^= 1) {
+    float (*sI)[kFTI + 4] = sI0 + buf * DIM;
+    unsigned long long acc2[UT][4];  // [user][item pair], packed (even item, odd item)
+#pragma unroll
+    for (int i = 0; i < UT; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc2[i][j] = 0ull;
+#pragma unroll 4
+    for (int d = 0; d < DIM; ++d) {
+      float av[UT];
+#pragma unroll
+      for (int h = 0; h < UT / 4; ++h) {
+        const float4 a = *reinterpret_cast<const float4*>(&sU[d][ty * UT + h * 4]);
+        av[h * 4 + 0] = a.x; av[h * 4 + 1] = a.y; av[h * 4 + 2] = a.z; av[h * 4 + 3] = a.w;
+      }
+      const ulonglong2 b0 = *reinterpret_cast<const ulonglong2*>(&sI[d][tx * 4]);
+      const ulonglong2 b1 = *reinterpret_cast<const ulonglong2*>(&sI[d][64 + tx * 4]);
+      const unsigned long long bv[4] = {b0.x, b0.y, b1.x, b1.y};
+#pragma unroll
+      for (int i = 0; i < UT; ++i) {
+        const unsigned long long a2 = dup2(av[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc2[i][j] = ffma2(a2, bv[j], acc2[i][j]);
+      }
+    }
+    // tile t+1 (in registers since before this tile's loop) goes to the other buffer, tile t+2 takes the registers
+    if (ib + kFTI < n_items) stage(buf ^ 1);
+    if (ib + 2 * kFTI < n_items) fetch(ib + 2 * kFTI);
+
+    // ---- candidates: one float compare per score against the row's threshold value; survivors (a handful per
+    //      row and tile) get their exact 64-bit key and go to a small local list ----
+    unsigned long long pk[NS];
+    unsigned char pr[NS];
+    int np = 0;
+#pragma unroll
+    for (int i = 0; i < UT; ++i) {
+      const int row = ty * UT + i;
+      const bool row_ok = ub + row < u1;
+      // value of the row's k-th best so far (-inf while the buffer holds fewer than k); rows past the end never pass
+      const uint32_t th = (uint32_t)(thr[row] >> 32);
+      const float thf = row_ok ? (th ? key_float(th) : -INFINITY) : INFINITY;
+      float mv[8];
+      if (MUL) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int it0 = ib + h * 64 + tx * 4;
+          const float* mp = mul + (ub + row - u0) * ldmul + it0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) mv[h * 4 + q] = (row_ok && it0 + q < n_items) ? __ldg(mp + q) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const unsigned long long p2 = acc2[i][j >> 1];
+        const float sc = __uint_as_float((j & 1) ? (uint32_t)(p2 >> 32) : (uint32_t)(p2 & 0xffffffffull));
+        const float v = MUL ? sc * mv[j] : sc;
+        if (v >= thf) {
+          const int item = ib + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+          if (item < n_items) {
+            pk[np] = make_key(float_key(v), (uint32_t)item);
+            pr[np] = (unsigned char)row;
+            ++np;
           }
         }
       }
     }
-  };
-  stream(0xffffffffu, 0xffffffffu);
-
-  for (int round = 0; round < k; ++round) {
-    const bool has = lc[0] != 0u;
-    const uint32_t mv = __reduce_max_sync(0xffffffffu, has ? lv[0] : 0u);
-    const uint32_t mc = __reduce_max_sync(0xffffffffu, (has && lv[0] == mv) ? lc[0] : 0u);
-    if (mc == 0u) {  // fewer than k selectable columns
-      if (lane == 0)
-        for (int t = round; t < k; ++t) {
-          out_idx[r * k + t] = -1;
-          if (out_val) out_val[r * k + t] = -INFINITY;
-        }
-      break;
+    while (true) {
+      int keep = 0;
+      for (int q = 0; q < np; ++q) {
+        const unsigned long long key = pk[q];
+        const int row = pr[q];
+        if (key <= thr[row]) continue;
+        const int slot = atomicAdd(&cnt[row], 1);
+        if (slot < CAP) { cand[(size_t)row * CAP + slot] = key; continue; }
+        pk[keep] = key; pr[keep] = (unsigned char)row; ++keep;
+      }
+      np = keep;
+      // the one barrier of the tile: every thread is past the FMA loop and has staged its part of the next tile
+      if (!__syncthreads_or(np > 0)) break;
+      for (int rr = 0; rr < TU / 8; ++rr) {  // each warp compacts the full buffers among its TU/8 rows
+        const int row = warp * (TU / 8) + rr;
+        if (cnt[row] >= CAP) compact_row(row, CAP);
+      }
+      __syncthreads();
     }
-    if (has && lv[0] == mv && lc[0] == mc) {  // exactly one lane
-      out_idx[r * k + round] = (int64_t)(mc - 1u);
-      if (out_val) out_val[r * k + round] = key_float(mv);
-#pragma unroll
-      for (int i = 0; i < LIST - 1; ++i) { lv[i] = lv[i + 1]; lc[i] = lc[i + 1]; }
-      lv[LIST - 1] = 0u; lc[LIST - 1] = 0u;
-      if (lc[0] == 0u) stream(mv, mc);  // list ran dry: refill with this lane's pairs below the popped one
+  }
+
+  for (int rr = 0; rr < TU / 8; ++rr) {
+    const int row = warp * (TU / 8) + rr;
+    const int64_t u = ub + row;
+    if (u >= u1) continue;
+    int c = cnt[row];
+    c = c < CAP ? c : CAP;
+    const int kept = compact_row(row, c);
+    for (int i = lane; i < k; i += 32) {
+      const unsigned long long key = cand[(size_t)row * CAP + i];
+      out_idx[(u - u0) * k + i] = i < kept ? (int64_t)(uint32_t)(key & 0xffffffffull) : -1;
+      if (out_val) out_val[(u - u0) * k + i] = i < kept ? key_float((uint32_t)(key >> 32)) : -INFINITY;
     }
   }
 }
@@ -239,13 +505,63 @@ extern "C" int lgc_topk_rows(const float* S, int64_t n_rows, int64_t n_cols, int
   LGC_REQUIRE(((uintptr_t)excl_mask & 3) == 0, "topk: mask must be 4-byte aligned");
   const unsigned grid = (unsigned)ceil_div(n_rows, kTopkWarps);
   cudaStream_t st = (cudaStream_t)stream;
-  if (k <= 32)
-    topk_rows_kernel<4><<<grid, kTopkWarps * 32, 0, st>>>(S, (int)n_rows, (int)n_cols, lds, excl_mask, mask_stride_bits,
-                                                          row_offset, k, out_idx, out_val);
-  else
-    topk_rows_kernel<8><<<grid, kTopkWarps * 32, 0, st>>>(S, (int)n_rows, (int)n_cols, lds, excl_mask, mask_stride_bits,
-                                                          row_offset, k, out_idx, out_val);
+  const bool vec = (lds & 3) == 0 && ((uintptr_t)S & 15) == 0;  // every row starts 16-byte aligned
+#define LGC_TOPK_LAUNCH(CAPV, VECV)                                                                          \
+  topk_rows_kernel<CAPV, VECV><<<grid, kTopkWarps * 32, 0, st>>>(S, (int)n_rows, (int)n_cols, lds, excl_mask, \
+                                                                 mask_stride_bits, row_offset, k, out_idx, out_val)
+  if (k <= 32) {
+    if (vec) LGC_TOPK_LAUNCH(64, true); else LGC_TOPK_LAUNCH(64, false);
+  } else {
+    if (vec) LGC_TOPK_LAUNCH(256, true); else LGC_TOPK_LAUNCH(256, false);
+  }
+#undef LGC_TOPK_LAUNCH
   LGC_LAUNCH_CHECK("topk_rows_kernel");
+  return LGC_OK;
+}
+
+extern "C" int lgc_score_topk(const float* Xu, const float* Xi, int64_t u0, int64_t u1, int64_t n_items, int32_t dim,
+                              const int32_t* seen_ptr, const int32_t* seen_idx, float fill, int32_t exclude_seen,
+                              const float* mul, int64_t ldmul, int32_t k, int64_t* out_idx, float* out_val,
+                              lgc_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LGC_REQUIRE(Xu && Xi && out_idx, "score_topk: null pointer");
+  LGC_REQUIRE(u0 >= 0 && u1 > u0 && n_items > 0 && n_items < (1ll << 31) - kFTI, "score_topk: bad extents");
+  LGC_REQUIRE(k >= 1 && k <= kTopkMaxK && k <= n_items, "score_topk: k must be in [1, min(128, n_items)]");
+  LGC_REQUIRE(((uintptr_t)Xu & 15) == 0 && ((uintptr_t)Xi & 15) == 0, "score_topk: embeddings must be 16-byte aligned");
+  LGC_REQUIRE((seen_ptr == nullptr) == (seen_idx == nullptr), "score_topk: seen_ptr / seen_idx mismatch");
+  LGC_REQUIRE(!mul || ldmul >= n_items, "score_topk: multiplier leading dimension smaller than the row");
+#define LGC_ST_LAUNCH(D, TUV, CAPV, MULV)                                                                       \
+  do {                                                                                                          \
+    static bool attr = false;                                                                                   \
+    constexpr size_t smem = score_topk_smem<D, TUV, CAPV>();                                                    \
+    if (!attr) {                                                                                                \
+      LGC_CUDA(cudaFuncSetAttribute(score_topk_kernel<D, TUV, CAPV, MULV>,                                      \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                   \
+      attr = true;                                                                                              \
+    }                                                                                                           \
+    score_topk_kernel<D, TUV, CAPV, MULV><<<(unsigned)ceil_div(u1 - u0, TUV), kFThreads, smem, stream>>>(       \
+        Xu, Xi, u0, u1, (int)n_items, seen_ptr, seen_idx, fill, exclude_seen, mul, ldmul, k, out_idx, out_val); \
+  } while (0)
+  // 128-user tiles (8 x 8 register tile) while the candidate buffers fit; small problems keep 64-user tiles so
+  // that the grid still covers the SMs
+  const bool big = (u1 - u0) >= (int64_t)128 * num_sms();
+#define LGC_ST_DIM(D)                                                                                           \
+  do {                                                                                                          \
+    if (k <= 32) {                                                                                              \
+      if (big) { if (mul) LGC_ST_LAUNCH(D, 128, 64, true); else LGC_ST_LAUNCH(D, 128, 64, false); }             \
+      else { if (mul) LGC_ST_LAUNCH(D, 64, 64, true); else LGC_ST_LAUNCH(D, 64, 64, false); }                   \
+    } else {                                                                                                    \
+      if (mul) LGC_ST_LAUNCH(D, 64, 256, true); else LGC_ST_LAUNCH(D, 64, 256, false);                          \
+    }                                                                                                           \
+  } while (0)
+  switch (dim) {
+    case 32: LGC_ST_DIM(32); break;
+    case 64: LGC_ST_DIM(64); break;
+    default: LGC_FAIL(LGC_ERR_UNSUPPORTED, "score_topk: embedding dim %d not in {32,64}", dim);
+  }
+#undef LGC_ST_DIM
+#undef LGC_ST_LAUNCH
+  LGC_LAUNCH_CHECK("score_topk_kernel");
   return LGC_OK;
 }
 

@@ -1,0 +1,100 @@
+// select.cuh — building blocks of the exact top-k selection shared by lgc_topk_rows and the
+// fused lgc_score_topk (score_topk.cu).
+//
+// A candidate is the 64-bit key  (monotone fp32 value key << 32) | column : larger key = better,
+// all keys of one row are distinct, so "k largest keys, descending" is the deterministic total
+// order (value descending, equal values -> larger column first) that np.argsort(row)[::-1]
+// produces on the reference's CPU path (/root/reference/model/SpreadMethod/recommend.py:38;
+// SURVEY.md §4).  Key 0 never occurs for a real value (-inf maps to 0x007FFFFF) and marks an
+// empty slot.
+//
+// Selection scheme ("threshold + candidate buffer"): a row keeps a buffer of CAP >= 2k keys and a
+// threshold = its current k-th largest key.  Streaming values are compared against the threshold
+// (one 32-bit compare in the hot loop); only the survivors are appended.  When the buffer is
+// full, one warp sorts it in registers (bitonic network, CAP/32 keys per lane), keeps the k best
+// and raises the threshold.  With n columns a row appends ~k ln(n/k) keys in total, so the
+// selection costs almost nothing next to reading (or computing) the values.
+#pragma once
+#include "common.cuh"
+
+namespace lgc {
+
+__device__ __forceinline__ uint32_t float_key(float x) {
+  const uint32_t b = __float_as_uint(x + 0.0f);       // -0.0 -> +0.0: the two zeros are ONE value (np.argsort ties)
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);  // monotone: larger float -> larger key
+}
+__device__ __forceinline__ float key_float(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+__device__ __forceinline__ unsigned long long make_key(uint32_t vkey, uint32_t col) {
+  return ((unsigned long long)vkey << 32) | (unsigned long long)col;
+}
+
+// Sort 32*E keys held as r[e] <-> logical index e*32 + lane, DESCENDING (index 0 = largest).
+template <int E>
+__device__ __forceinline__ void warp_sort_desc(unsigned long long (&r)[E], int lane) {
+  constexpr int N = 32 * E;
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+        const int je = j >> 5;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          if ((e & je) == 0) {
+            const int e2 = e | je;
+            const bool dir = ((e << 5) & k) == 0;  // block sorted "descending" when dir
+            const unsigned long long a = r[e], b = r[e2];
+            const unsigned long long hi = a > b ? a : b, lo = a > b ? b : a;
+            r[e] = dir ? hi : lo;
+            r[e2] = dir ? lo : hi;
+          }
+        }
+      } else {
+        const bool lower = (lane & j) == 0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int idx_hi = e << 5;  // k may exceed 32: the direction bit can sit in e or in lane
+          const bool dir = k >= 32 ? ((idx_hi & k) == 0) : ((lane & k) == 0);
+          const unsigned long long a = r[e];
+          const unsigned long long b = __shfl_xor_sync(0xffffffffu, a, j);
+          const bool keep_max = (dir == lower);
+          r[e] = keep_max ? (a > b ? a : b) : (a > b ? b : a);
+        }
+      }
+    }
+  }
+}
+
+// One warp: keep the k largest of the first `cnt` keys of buf (cnt <= 32*E), sorted descending in
+// buf[0..k); returns the new count (the non-zero keys among them).  *thr becomes the k-th largest key (0 while
+// fewer than k keys exist).  Every lane must call it; buf may be written by other warps before the
+// caller's preceding barrier only.
+template <int E>
+__device__ __forceinline__ int warp_compact(unsigned long long* buf, int cnt, int k, int lane,
+                                            unsigned long long* thr) {
+  __syncwarp();
+  unsigned long long r[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int idx = e * 32 + lane;
+    r[e] = idx < cnt ? buf[idx] : 0ull;
+  }
+  warp_sort_desc<E>(r, lane);
+  __syncwarp();
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int idx = e * 32 + lane;
+    if (idx < k) buf[idx] = r[e];
+  }
+  __syncwarp();
+  int nz = 0;  // zero keys (empty / dropped entries) sort last and are not kept
+#pragma unroll
+  for (int e = 0; e < E; ++e) nz += (e * 32 + lane < k && r[e] != 0ull) ? 1 : 0;
+  const int kept = __reduce_add_sync(0xffffffffu, nz);
+  *thr = kept == k ? buf[k - 1] : 0ull;
+  return kept;
+}
+
+}  // namespace lgc

@@ -121,86 +121,127 @@ __global__ void scale_prep_kernel(const int32_t* __restrict__ ki, int64_t n, dou
   inv_b[i] = inv_or_one(pow(k, lambda));
 }
 
-// column maxima of W = G / (k_i^(1-l) k_j^l): cmax[j] = max_i W[i,j] (W >= 0), fp32 is enough — the
-// value only selects a power-of-two scale.  grid (n/32 column blocks, row strips of 256).
+// column maxima of W = G / (k_i^(1-l) k_j^l): cmax[j] = max_i G[i,j] inv_a[i] (W >= 0; the column factor is
+// applied by the consumer).  fp32 is enough — the value only selects a power-of-two scale.
+// grid (column strips of 128, row chunks of 256); a warp reads 512 contiguous bytes per row (float4 per lane).
+constexpr int kCmCols = 128, kCmRows = 256;
+
 __global__ void __launch_bounds__(256)
 colmax_w_kernel(const float* __restrict__ G, int64_t ldg, int64_t n, const double* __restrict__ inv_a,
-                const double* __restrict__ inv_b, unsigned int* __restrict__ cmax_bits) {
-  __shared__ float sa[256];
-  __shared__ float smax[8][32];
-  const int64_t j = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
-  const int64_t i0 = (int64_t)blockIdx.y * 256;
+                unsigned int* __restrict__ cmax_bits) {
+  __shared__ float sa[kCmRows];
+  __shared__ float4 smax[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t j = (int64_t)blockIdx.x * kCmCols + lane * 4;
+  const int64_t i0 = (int64_t)blockIdx.y * kCmRows;
   {
     const int64_t i = i0 + threadIdx.x;
-    sa[threadIdx.x] = i < n ? (float)inv_a[i] : 1.f;
+    sa[threadIdx.x] = i < n ? (float)inv_a[i] : 0.f;
   }
   __syncthreads();
-  const int ty = threadIdx.x >> 5;
-  float m = 0.f;
+  float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool vec = (ldg & 3) == 0 && ((uintptr_t)G & 15) == 0 && j + 3 < n;
   if (j < n) {
-    const float b = (float)inv_b[j];
-    for (int r = ty; r < 256 && i0 + r < n; r += 8) m = fmaxf(m, G[(i0 + r) * ldg + j] * sa[r] * b);
+#pragma unroll 8
+    for (int r = w; r < kCmRows; r += 8) {
+      const int64_t i = i0 + r;
+      if (i >= n) break;
+      float4 g;
+      if (vec) {
+        g = __ldg(reinterpret_cast<const float4*>(G + i * ldg + j));
+      } else {
+        g.x = G[i * ldg + j];
+        g.y = j + 1 < n ? G[i * ldg + j + 1] : 0.f;
+        g.z = j + 2 < n ? G[i * ldg + j + 2] : 0.f;
+        g.w = j + 3 < n ? G[i * ldg + j + 3] : 0.f;
+      }
+      const float a = sa[r];
+      m.x = fmaxf(m.x, g.x * a); m.y = fmaxf(m.y, g.y * a); m.z = fmaxf(m.z, g.z * a); m.w = fmaxf(m.w, g.w * a);
+    }
   }
-  smax[ty][threadIdx.x & 31] = m;
+  smax[w][lane] = m;
   __syncthreads();
-  if (ty == 0 && j < n) {
+  if (w == 0 && j < n) {
 #pragma unroll
-    for (int w = 1; w < 8; ++w) m = fmaxf(m, smax[w][threadIdx.x]);
-    atomicMax(cmax_bits + j, __float_as_uint(m));  // non-negative floats order like their bit patterns
+    for (int q = 1; q < 8; ++q) {
+      const float4 o = smax[q][lane];
+      m.x = fmaxf(m.x, o.x); m.y = fmaxf(m.y, o.y); m.z = fmaxf(m.z, o.z); m.w = fmaxf(m.w, o.w);
+    }
+    // non-negative floats order like their bit patterns
+    atomicMax(cmax_bits + j, __float_as_uint(m.x));
+    if (j + 1 < n) atomicMax(cmax_bits + j + 1, __float_as_uint(m.y));
+    if (j + 2 < n) atomicMax(cmax_bits + j + 2, __float_as_uint(m.z));
+    if (j + 3 < n) atomicMax(cmax_bits + j + 3, __float_as_uint(m.w));
   }
 }
 
 // W = G / (k_i^(1-l) k_j^l) quantised per column j to `digits` base-256 digits of
-// q = round(W / s_j * 256^digits), s_j = the power of two strictly above cmax[j]; digit planes are
-// written transposed (plane[d][j, i], K = source item i contiguous) for the u8 F = A.W GEMM, and
-// cs[j] = s_j / 256^digits is the epilogue column scale.  Same 32x32 tiling as scale_w_kernel.
+// q = round(W / s_j * 256^digits), s_j = the power of two strictly above the column maximum; the digit planes
+// are written transposed (plane[d][j, i], K = source item i contiguous) for the u8 F = A.W GEMM, and
+// cs[j] = s_j / 256^digits is the epilogue column scale.  One CTA quantises a 128 (i) x 64 (j) tile (256 B
+// row segments of G), transposes it through shared memory and stores four source items per 32-bit word, so
+// every plane row receives 128 contiguous bytes.
+constexpr int kSwCols = 64, kSwRows = 128, kSwLd = kSwRows + 4;
+
 __global__ void __launch_bounds__(256)
 scale_w_u8_kernel(const float* __restrict__ G, int64_t ldg, int64_t n, const double* __restrict__ inv_a,
-                  const double* __restrict__ inv_b, const unsigned int* __restrict__ cmax_bits, float* __restrict__ W32, int64_t ldw,
-                  uint8_t* __restrict__ Wt, int64_t ldk, int64_t plane_stride, int digits, float* __restrict__ cs) {
-  __shared__ unsigned int tile[32][33];
-  __shared__ double sa[32], sb[32], sinv[32];
-  const double qmax = ldexp(1.0, 8 * digits) - 1.0;
-  const int64_t i0 = (int64_t)blockIdx.y * 32, j0 = (int64_t)blockIdx.x * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  if (threadIdx.x < 32) {
+                  const double* __restrict__ inv_b, const unsigned int* __restrict__ cmax_bits,
+                  float* __restrict__ W32, int64_t ldw, uint8_t* __restrict__ Wt, int64_t ldk,
+                  int64_t plane_stride, int digits, float* __restrict__ cs) {
+  __shared__ __align__(16) unsigned int tile[kSwCols][kSwLd];
+  __shared__ double sa[kSwRows], sb[kSwCols], sinv[kSwCols];
+  const int64_t j0 = (int64_t)blockIdx.x * kSwCols, i0 = (int64_t)blockIdx.y * kSwRows;
+  if (threadIdx.x < kSwRows) {
     const int64_t i = i0 + threadIdx.x;
-    sa[threadIdx.x] = i < n ? inv_a[i] : 1.0;
-  } else if (threadIdx.x < 64) {
-    const int t = threadIdx.x - 32;
+    sa[threadIdx.x] = i < n ? inv_a[i] : 0.0;
+  } else if (threadIdx.x < kSwRows + kSwCols) {
+    const int t = threadIdx.x - kSwRows;
     const int64_t j = j0 + t;
-    sb[t] = j < n ? inv_b[j] : 1.0;
-    // s_j = 2^(e+1) with 2^e <= cmax < 2^(e+1)  (1.0 for an all-zero column); a 1 ulp head-room covers the
+    const double b = j < n ? inv_b[j] : 1.0;
+    // s_j = 2^(e+1) with 2^e <= cmax < 2^(e+1) (1.0 for an all-zero column); 1 ulp of head-room covers the
     // fp32 evaluation of the maximum
     double s = 1.0;
     if (j < n) {
-      const float cm = __uint_as_float(cmax_bits[j]) * 1.000001f;
+      const float cm = __uint_as_float(cmax_bits[j]) * (float)b * 1.000001f;
       if (cm > 0.f) { int e; frexp((double)cm, &e); s = ldexp(1.0, e); }
       if (blockIdx.y == 0 && cs) cs[j] = (float)ldexp(s, -8 * digits);
     }
+    sb[t] = b;
     sinv[t] = ldexp(1.0 / s, 8 * digits);
   }
   __syncthreads();
-#pragma unroll
-  for (int r = ty; r < 32; r += 8) {
-    const int64_t i = i0 + r, j = j0 + tx;
+  const double qmax = ldexp(1.0, 8 * digits) - 1.0;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 columns x 4 row lanes
+  const int64_t j = j0 + tx;
+  const double bj = sb[tx], sj = sinv[tx];
+#pragma unroll 8
+  for (int r = ty; r < kSwRows; r += 4) {
+    const int64_t i = i0 + r;
     unsigned int qi = 0u;
     if (i < n && j < n) {
-      const double w = (double)G[i * ldg + j] * sa[r] * sb[tx];
+      const double w = (double)__ldg(G + i * ldg + j) * sa[r] * bj;
       if (W32) W32[i * ldw + j] = (float)w;
-      double q = rint(w * sinv[tx]);
+      double q = rint(w * sj);
       q = q < 0.0 ? 0.0 : (q > qmax ? qmax : q);
       qi = (unsigned int)q;
     }
-    tile[r][tx] = qi;
+    tile[tx][r] = qi;
   }
   __syncthreads();
+  // thread -> (column c, group g of four source items): lanes run over g, so a warp stores 128 contiguous bytes
 #pragma unroll
-  for (int r = ty; r < 32; r += 8) {
-    const int64_t j = j0 + r, i = i0 + tx;
-    if (i < n && j < n) {
-      const unsigned int qi = tile[tx][r];
-      for (int d = 0; d < digits; ++d) Wt[d * plane_stride + j * ldk + i] = (uint8_t)((qi >> (8 * d)) & 255u);
+  for (int t = 0; t < (kSwCols * kSwRows / 4) / 256; ++t) {
+    const int p = threadIdx.x + 256 * t;
+    const int c = p >> 5, g = p & 31;
+    if (j0 + c < n && i0 + 4 * g < ldk) {
+      const uint4 q4 = *reinterpret_cast<const uint4*>(&tile[c][4 * g]);
+      uint8_t* dst = Wt + (j0 + c) * ldk + i0 + 4 * g;
+      for (int d = 0; d < digits; ++d) {
+        const int sh = 8 * d;
+        const unsigned int word = ((q4.x >> sh) & 255u) | (((q4.y >> sh) & 255u) << 8) |
+                                  (((q4.z >> sh) & 255u) << 16) | (((q4.w >> sh) & 255u) << 24);
+        *reinterpret_cast<unsigned int*>(dst + d * plane_stride) = word;
+      }
     }
   }
 }
@@ -293,17 +334,19 @@ extern "C" int hs_scale_w_u8(const float* G, int64_t ldg, int64_t n, const int32
   LGC_REQUIRE(((uintptr_t)scratch & 7) == 0, "scale_w_u8: scratch must be 8-byte aligned");
   double* inv_a = (double*)scratch;          // scratch layout: n doubles, n doubles, n uint32
   double* inv_b = inv_a + n;
-  uint32_t* colmax_scratch = (uint32_t*)(inv_b + n);
   LGC_REQUIRE(digits >= 1 && digits <= 4 && ldk >= n, "scale_w_u8: digits in 1..4, ldk >= n");
   LGC_REQUIRE(digits == 1 || plane_stride >= n * ldk, "scale_w_u8: plane stride overlaps planes");
   LGC_REQUIRE(!W32 || ldw >= n, "scale_w_u8: ldw < n");
+  LGC_REQUIRE((ldk & 3) == 0 && (plane_stride & 3) == 0 && ((uintptr_t)Wt_digits & 3) == 0,
+              "scale_w_u8: digit planes must be 4-byte aligned with ldk and plane stride multiples of 4");
+  uint32_t* colmax_scratch = (uint32_t*)(inv_b + n);
   LGC_CUDA(cudaMemsetAsync(colmax_scratch, 0, sizeof(uint32_t) * (size_t)n, stream));
   scale_prep_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(ki, n, lambda, inv_a, inv_b);
   LGC_LAUNCH_CHECK("scale_prep_kernel");
-  dim3 g1((unsigned)ceil_div(n, 32), (unsigned)ceil_div(n, 256));
-  colmax_w_kernel<<<g1, 256, 0, stream>>>(G, ldg, n, inv_a, inv_b, colmax_scratch);
+  dim3 g1((unsigned)ceil_div(n, kCmCols), (unsigned)ceil_div(n, kCmRows));
+  colmax_w_kernel<<<g1, 256, 0, stream>>>(G, ldg, n, inv_a, colmax_scratch);
   LGC_LAUNCH_CHECK("colmax_w_kernel");
-  dim3 g2((unsigned)ceil_div(n, 32), (unsigned)ceil_div(n, 32));
+  dim3 g2((unsigned)ceil_div(n, kSwCols), (unsigned)ceil_div(n, kSwRows));
   scale_w_u8_kernel<<<g2, 256, 0, stream>>>(G, ldg, n, inv_a, inv_b, colmax_scratch, W32, ldw, Wt_digits, ldk,
                                            plane_stride, digits, col_scale);
   LGC_LAUNCH_CHECK("scale_w_u8_kernel");

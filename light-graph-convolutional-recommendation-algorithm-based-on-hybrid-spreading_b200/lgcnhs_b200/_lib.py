@@ -38,6 +38,7 @@ _SIGS = {
     "lgc_adam_step": (C.c_int, [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _p]),
     "lgc_score_block": (C.c_int, [_p, _p, _i64, _i64, _i64, _i32, _p, _p, _f32, _p, _i64, _p]),
     "lgc_topk_rows": (C.c_int, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i32, _p, _p, _p]),
+    "lgc_score_topk": (C.c_int, [_p, _p, _i64, _i64, _i64, _i32, _p, _p, _f32, _i32, _p, _i64, _i32, _p, _p, _p]),
     "lgc_mask_from_csr": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _p]),
     "hs_degrees": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p]),
     "hs_pack_a": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _i64, _p]),

@@ -32,10 +32,19 @@ def allocate_score_device(model, user_num: int, item_num: int, train_data_df: pd
 
 def fused_recommend(model, user_num: int, item_num: int, train_data_df: pd.DataFrame, val_data_df: pd.DataFrame,
                     lambda_val: float, k: int) -> torch.Tensor:
-    """top-k of (G_score ⊙ A.HybridS(lambda)) with train+val items filtered, all on the device."""
-    G_score = allocate_score_device(model, user_num, item_num, train_data_df, val_data_df)
-    eng = engine_from_frames(user_num, item_num, train_data_df, val_data_df)
-    idx, _ = eng.recommend(float(lambda_val), k, filtered=True, gscore=G_score)
+    """top-k of (G_score ⊙ A.HybridS(lambda)) with train+val items filtered, all on the device.  G_score is never
+    materialised: the layer-0 score tiles are multiplied with F and selected inside one kernel (lgc_score_topk)."""
+    dev = cuda_device()
+    model = model.to(dev)
+    xu = model.users_emb.weight.detach().contiguous()
+    xi = model.items_emb.weight.detach().contiguous()
+    u, i = interactions_from_frames(train_data_df, val_data_df)
+    seen = ops.seen_csr(u, i, user_num, item_num)
+    eng = ops.SpreadingEngine(user_num, item_num, u, i)
+    eng.general_w()
+    eng.scale(float(lambda_val))
+    F = eng.resource()
+    idx, _ = ops.score_topk(xu, xi, k, seen, fill=-float(1 << 10), exclude_seen=True, mul=F, want_values=False)
     return idx
 
 

@@ -223,6 +223,27 @@ def score_block(Xu: torch.Tensor, Xi: torch.Tensor, u0: int, u1: int, seen: Opti
     return out
 
 
+def score_topk(Xu: torch.Tensor, Xi: torch.Tensor, k: int, seen: Optional[tuple] = None, fill: float = -1024.0,
+               exclude_seen: bool = False, mul: Optional[torch.Tensor] = None, u0: int = 0, u1: Optional[int] = None,
+               want_values: bool = True):
+    """Fused  top-k_i ( (seen ? fill : <Xu[u], Xi[i]>) * mul[u, i] )  for users [u0, u1): the score matrix is never
+    materialised (reference: matmul + index_put(-1024) + topk, model/LightGCN/recommend.py:86-114)."""
+    Xu = _req(Xu, torch.float32, "Xu")
+    Xi = _req(Xi, torch.float32, "Xi")
+    M, dim = int(Xi.shape[0]), int(Xi.shape[1])
+    u1 = int(Xu.shape[0]) if u1 is None else u1
+    sp, si = (None, None) if seen is None else seen
+    if mul is not None:
+        if mul.dtype != torch.float32 or not mul.is_cuda or mul.stride(1) != 1 or mul.shape[0] != u1 - u0 or mul.shape[1] != M:
+            raise LgcnhsError("score_topk: mul must be a CUDA fp32 (u1-u0, n_items) matrix with unit column stride")
+    idx = torch.empty((u1 - u0, k), dtype=torch.int64, device=Xu.device)
+    val = torch.empty((u1 - u0, k), dtype=torch.float32, device=Xu.device) if want_values else None
+    check(lib().lgc_score_topk(_ptr(Xu), _ptr(Xi), u0, u1, M, dim, _ptr(sp), _ptr(si), float(fill), int(exclude_seen),
+                               _ptr(mul), int(mul.stride(0)) if mul is not None else 0, int(k), _ptr(idx), _ptr(val),
+                               _stream()), "score_topk")
+    return idx, val
+
+
 class ExclusionMask:
     """Bit-packed (n_rows x n_cols) matrix of entries that must never be recommended."""
 
@@ -363,21 +384,26 @@ class SpreadingEngine:
         shift = 8 * digits - 1 + int(math.floor(math.log2(kmin)))
         return digits, shift
 
-    def general_w(self, item_range: Optional[tuple[int, int]] = None) -> torch.Tensor:
-        """G = A^T K_u^-1 A (model/SpreadMethod/model.py:14-27) on the tensor cores."""
-        L = lib()
+    def pack_g_operands(self):
+        """(A^T as 0/1 uint8, digit planes Q_d of round(2^shift / k_u) A^T, shift): the K(=user)-major tensor-core
+        operands of G, standing in for `A.T / user_degrees` (model/SpreadMethod/model.py:21-25)."""
         U, M, dev = self.U, self.M, self.dev
-        j0, j1 = (0, M) if item_range is None else item_range
-        if self.g_kind == "u8":
-            ldU = _pad(U, 128)
-            digits, shift = self.fixed_point()
-            At = torch.zeros((M, ldU), dtype=torch.uint8, device=dev)
-            Q = torch.zeros((digits, M, ldU), dtype=torch.uint8, device=dev)
-            check(L.hs_pack_at(_ptr(self.users), _ptr(self.items), self.nnz, U, M, _ptr(self.ku), shift, digits,
+        ldU = _pad(U, 128)
+        digits, shift = self.fixed_point()
+        At = torch.zeros((M, ldU), dtype=torch.uint8, device=dev)
+        Q = torch.zeros((digits, M, ldU), dtype=torch.uint8, device=dev)
+        check(lib().hs_pack_at(_ptr(self.users), _ptr(self.items), self.nnz, U, M, _ptr(self.ku), shift, digits,
                                _ptr(At), _ptr(Q), ldU, M * ldU, _stream()), "pack_at")
-            G = gemm_planes(1, At, Q[:, j0:j1], M, j1 - j0, U, scale=2.0 ** (-shift))
-        else:
+        return At, Q, shift
+
+    def general_w(self, item_range: Optional[tuple[int, int]] = None, operands=None,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """G = A^T K_u^-1 A (model/SpreadMethod/model.py:14-27) on the tensor cores (exact int8 fixed point)."""
+        if self.g_kind != "u8":
             raise LgcnhsError("g_kind must be 'u8'")
+        j0, j1 = (0, self.M) if item_range is None else item_range
+        At, Q, shift = self.pack_g_operands() if operands is None else operands
+        G = gemm_planes(1, At, Q[:, j0:j1], self.M, j1 - j0, self.U, out=out, scale=2.0 ** (-shift))
         if item_range is None:
             self.G = G
         return G

@@ -9,21 +9,15 @@ from utils.graph import convertAdjMatrixToEdgeIndex
 
 def _topk_layer0(model, user_num: int, item_num: int, exclude_edge_indices, k: int) -> torch.Tensor:
     """score = e_u^0 . e_i^0^T (LAYER-0 weights, reference evaluation.py:31-34 / recommend.py:83-86),
-    seen pairs set to -1024, top-k — computed block-wise so the (U, M) matrix never exists."""
+    seen pairs set to -1024, top-k — one fused kernel, the (U, M) matrix never exists."""
     xu = model.users_emb.weight.detach().contiguous()
     xi = model.items_emb.weight.detach().contiguous()
     dev = xu.device
     uu = torch.cat([e[0] for e in exclude_edge_indices]).to(dev)
     ii = torch.cat([e[1] for e in exclude_edge_indices]).to(dev)
     seen = ops.seen_csr(uu, ii, user_num, item_num)
-    blk = max(64, min(user_num, (1 << 28) // max(item_num, 1)))     # <= 1 GiB of scores per block
-    out = torch.empty((user_num, k), dtype=torch.int64, device=dev)
-    buf = torch.empty((min(blk, user_num), (item_num + 3) // 4 * 4), dtype=torch.float32, device=dev)
-    for u0 in range(0, user_num, blk):
-        u1 = min(u0 + blk, user_num)
-        s = ops.score_block(xu, xi, u0, u1, seen, fill=-float(1 << 10), out=buf[: u1 - u0, :item_num])
-        idx, _ = ops.topk_rows(s, k, want_values=False)
-        out[u0:u1] = idx
+    # one fused kernel: fp32-FMA score tiles -> seen rule -> per-row candidate buffers (lgc_score_topk)
+    out, _ = ops.score_topk(xu, xi, k, seen, fill=-float(1 << 10), want_values=False)
     return out
 
 

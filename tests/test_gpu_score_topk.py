@@ -116,3 +116,103 @@ def test_topk_refill_and_mask_offsets(dev):
         ref[ex_u[sel] - off, ex_i[sel]] = -float("inf")
         rv, ri = torch.topk(ref, k)
         assert torch.equal(val.cpu(), rv) and torch.equal(torch.gather(ref, 1, idx.cpu()), rv)
+
+
+# ------------------------------------------------------------------------------------------
+# fused score + seen rule + top-k (lgc_score_topk): the (U, M) matrix is never materialised
+# ------------------------------------------------------------------------------------------
+def _rand_problem(U, M, dim, seed, n_seen):
+    g = torch.Generator().manual_seed(seed)
+    uw = torch.empty(U, dim).normal_(std=0.1, generator=g)
+    iw = torch.empty(M, dim).normal_(std=0.1, generator=g)
+    su = torch.randint(U, (n_seen,), generator=g)
+    si = torch.randint(M, (n_seen,), generator=g)
+    return uw, iw, su, si
+
+
+@pytest.mark.parametrize("U,M,dim,k", [(943, 1682, 64, 20), (943, 1682, 64, 100), (130, 3706, 64, 10), (65, 100, 64, 32),
+                                       (7, 129, 32, 5), (200, 5000, 32, 128), (64, 128, 64, 128)])
+def test_score_topk_equals_unfused(dev, U, M, dim, k):
+    """Same FMA order as lgc_score_block, same selection rule as lgc_topk_rows -> bit-identical ids and values;
+    and the reference semantics (matmul, score[seen] = -1024, torch.topk; model/LightGCN/recommend.py:86-114)."""
+    from lgcnhs_b200 import ops
+
+    uw, iw, su, si = _rand_problem(U, M, dim, U * 7 + M, 20 * U)
+    seen = ops.seen_csr(su.to(dev), si.to(dev), U, M)
+    dense = ops.score_block(uw.to(dev), iw.to(dev), 0, U, seen)
+    ridx, rval = ops.topk_rows(dense, k)
+    idx, val = ops.score_topk(uw.to(dev), iw.to(dev), k, seen)
+    assert torch.equal(val, rval) and torch.equal(idx, ridx)
+    # the CPU statement of the reference rule
+    ref = uw @ iw.T
+    ref[su, si] = -1024.0
+    rv, _ = torch.topk(ref, k)
+    assert_close(val, rv, "fused top-k scores")
+    # a user sub-range with an odd offset
+    if U > 70:
+        idx2, val2 = ops.score_topk(uw.to(dev), iw.to(dev), k, seen, u0=37, u1=U - 5)
+        assert torch.equal(idx2, ridx[37:U - 5]) and torch.equal(val2, rval[37:U - 5])
+
+
+def test_score_topk_adversarial_orders(dev):
+    """Scores increasing with the item id (every new item beats the threshold: the buffers compact at the maximum
+    rate), decreasing, and all-equal (pure tie-break) rows."""
+    from lgcnhs_b200 import ops
+
+    U, M, k = 70, 4000, 20
+    uw = torch.zeros(U, 64)
+    iw = torch.zeros(M, 64)
+    uw[:, 0] = 1.0
+    uw[1::3, 0] = -1.0                                  # decreasing rows
+    uw[2::3, 0] = 0.0                                   # all-equal rows
+    iw[:, 0] = torch.arange(M, dtype=torch.float32) / M
+    idx, val = ops.score_topk(uw.to(dev), iw.to(dev), k)
+    ref = uw @ iw.T
+    rv, _ = torch.topk(ref, k)
+    assert torch.equal(val.cpu(), rv)
+    idx = idx.cpu()
+    assert idx[0].tolist() == list(range(M - 1, M - 1 - k, -1))
+    assert idx[1].tolist() == list(range(0, k)) or torch.equal(torch.gather(ref, 1, idx)[1], rv[1])
+    assert idx[2].tolist() == list(range(M - 1, M - 1 - k, -1))      # ties -> larger index first
+
+
+def test_score_topk_fused_hadamard_and_exclusion(dev):
+    """F1: top-k of (G_score * F) with seen items dropped == reference getResourceMat + recommendForAllUser
+    (model/SpreadLightGCN/model.py:151, recommend.py:34-46)."""
+    from lgcnhs_b200 import ops
+
+    U, M, k = 150, 2100, 30
+    uw, iw, su, si = _rand_problem(U, M, 64, 5, 3000)
+    g = torch.Generator().manual_seed(9)
+    F = torch.rand(U, M, generator=g)
+    F[F < 0.5] = 0.0
+    seen = ops.seen_csr(su.to(dev), si.to(dev), U, M)
+    idx, val = ops.score_topk(uw.to(dev), iw.to(dev), k, seen, exclude_seen=True, mul=F.to(dev))
+    # unfused device path: masked score, Hadamard, filtered top-k
+    dense = ops.score_block(uw.to(dev), iw.to(dev), 0, U, seen) * F.to(dev)
+    excl = ops.ExclusionMask.from_csr(seen, U, M)
+    ridx, rval = ops.topk_rows(dense.contiguous(), k, excl)
+    assert torch.equal(val, rval) and torch.equal(idx, ridx)
+    # reference rule in float64 on the host
+    G = (uw @ iw.T).double()
+    G[su, si] = -1024.0
+    Fn = G * F.double()
+    Fn[su, si] = -np.inf
+    rv, ri = torch.topk(Fn, k)
+    assert_close(val, rv.float(), "fused Hadamard top-k scores")
+    seen_set = set(zip(su.tolist(), si.tolist()))
+    assert not any((u, int(i)) in seen_set for u in range(U) for i in idx[u].cpu())
+
+
+@pytest.mark.parametrize("k", [20, 50, 100])
+def test_score_topk_large_user_tiles(dev, k):
+    """>= 128 * n_sms users selects the 128-user CTA tile (8 x 8 register tile); k = 100 falls back to 64-user tiles."""
+    from lgcnhs_b200 import ops
+
+    U, M = 19100, 389
+    uw, iw, su, si = _rand_problem(U, M, 64, 77, 40000)
+    seen = ops.seen_csr(su.to(dev), si.to(dev), U, M)
+    dense = ops.score_block(uw.to(dev), iw.to(dev), 0, U, seen)
+    ridx, rval = ops.topk_rows(dense, k)
+    idx, val = ops.score_topk(uw.to(dev), iw.to(dev), k, seen)
+    assert torch.equal(val, rval) and torch.equal(idx, ridx)
