@@ -113,7 +113,7 @@ topk_rows_kernel(const float* __restrict__ S, int n_rows, int n, int64_t lds, co
 
   int cnt = 0;
   unsigned long long thr = 0ull;
-  uint32_t thr_hi = 0u;
+  float thr_f = -INFINITY;  // value of the current k-th best: the hot loop is ONE float compare per element
 
   // warp-collective: every lane offers one (value key, column) pair; `live` = column in range
   auto offer = [&](uint32_t vk, int c, bool live) {
@@ -127,7 +127,7 @@ topk_rows_kernel(const float* __restrict__ S, int n_rows, int n, int64_t lds, co
     if (m == 0u) return;
     if (cnt + __popc(m) > CAP) {
       cnt = warp_compact<E>(buf, cnt, k, lane, &thr);
-      thr_hi = (uint32_t)(thr >> 32);
+      thr_f = thr ? key_float((uint32_t)(thr >> 32)) : -INFINITY;
       pass = pass && key > thr;
       m = __ballot_sync(0xffffffffu, pass);
     }
@@ -160,7 +160,7 @@ topk_rows_kernel(const float* __restrict__ S, int n_rows, int n, int64_t lds, co
     const unsigned long long seed = __shfl_sync(0xffffffffu, best[0], k - 1);
     if (seed != 0ull) {
       thr = seed - 1ull;  // the seed element itself must still pass
-      thr_hi = (uint32_t)(thr >> 32);
+      thr_f = key_float((uint32_t)(seed >> 32));
     }
   }
 
@@ -170,7 +170,7 @@ topk_rows_kernel(const float* __restrict__ S, int n_rows, int n, int64_t lds, co
   constexpr int NV = VEC ? 16 : 8;
   constexpr int COLS = 32 * NV;
   for (int c0 = 0; c0 < n; c0 += COLS) {
-    uint32_t vk[NV];  // indexed dynamically in the slow path -> lives in local memory (L1), the fast path stays in registers
+    uint32_t vk[NV];  // raw value bits; indexed dynamically in the slow path -> lives in local memory (L1), the fast path stays in registers
     uint32_t bits = 0u;
     if (VEC) {
       float4 v[4];
@@ -184,9 +184,8 @@ topk_rows_kernel(const float* __restrict__ S, int n_rows, int n, int64_t lds, co
         const float f[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const uint32_t x = float_key(f[q]);
-          vk[u * 4 + q] = x;
-          if (c0 + u * 128 + lane * 4 + q < n && x >= thr_hi) bits |= 1u << (u * 4 + q);
+          vk[u * 4 + q] = __float_as_uint(f[q]);
+          if (f[q] >= thr_f && c0 + u * 128 + lane * 4 + q < n) bits |= 1u << (u * 4 + q);
         }
       }
     } else {
@@ -198,9 +197,8 @@ topk_rows_kernel(const float* __restrict__ S, int n_rows, int n, int64_t lds, co
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const uint32_t x = float_key(v[u]);
-        vk[u] = x;
-        if (c0 + u * 32 + lane < n && x >= thr_hi) bits |= 1u << u;
+        vk[u] = __float_as_uint(v[u]);
+        if (v[u] >= thr_f && c0 + u * 32 + lane < n) bits |= 1u << u;
       }
     }
 #pragma unroll 1
@@ -209,7 +207,7 @@ topk_rows_kernel(const float* __restrict__ S, int n_rows, int n, int64_t lds, co
       const int q = has ? __ffs(bits) - 1 : 0;
       bits &= bits - 1u;
       const int c = VEC ? c0 + (q >> 2) * 128 + lane * 4 + (q & 3) : c0 + q * 32 + lane;
-      offer(vk[q], c, has);
+      offer(float_key(__uint_as_float(vk[q])), c, has);
     }
   }
 

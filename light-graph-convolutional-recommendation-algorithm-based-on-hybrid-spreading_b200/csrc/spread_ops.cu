@@ -142,21 +142,31 @@ colmax_w_kernel(const float* __restrict__ G, int64_t ldg, int64_t n, const doubl
   float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
   const bool vec = (ldg & 3) == 0 && ((uintptr_t)G & 15) == 0 && j + 3 < n;
   if (j < n) {
-#pragma unroll 8
-    for (int r = w; r < kCmRows; r += 8) {
-      const int64_t i = i0 + r;
-      if (i >= n) break;
-      float4 g;
-      if (vec) {
-        g = __ldg(reinterpret_cast<const float4*>(G + i * ldg + j));
-      } else {
-        g.x = G[i * ldg + j];
-        g.y = j + 1 < n ? G[i * ldg + j + 1] : 0.f;
-        g.z = j + 2 < n ? G[i * ldg + j + 2] : 0.f;
-        g.w = j + 3 < n ? G[i * ldg + j + 3] : 0.f;
+    // 32 rows per thread, 8 independent 128-bit loads in flight at a time (no early exit inside a group)
+#pragma unroll 1
+    for (int r0 = w; r0 < kCmRows; r0 += 64) {
+      float4 g[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int64_t i = i0 + r0 + 8 * u;
+        g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n) {
+          if (vec) {
+            g[u] = __ldg(reinterpret_cast<const float4*>(G + i * ldg + j));
+          } else {
+            g[u].x = G[i * ldg + j];
+            g[u].y = j + 1 < n ? G[i * ldg + j + 1] : 0.f;
+            g[u].z = j + 2 < n ? G[i * ldg + j + 2] : 0.f;
+            g[u].w = j + 3 < n ? G[i * ldg + j + 3] : 0.f;
+          }
+        }
       }
-      const float a = sa[r];
-      m.x = fmaxf(m.x, g.x * a); m.y = fmaxf(m.y, g.y * a); m.z = fmaxf(m.z, g.z * a); m.w = fmaxf(m.w, g.w * a);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float a = sa[r0 + 8 * u];
+        m.x = fmaxf(m.x, g[u].x * a); m.y = fmaxf(m.y, g[u].y * a);
+        m.z = fmaxf(m.z, g[u].z * a); m.w = fmaxf(m.w, g[u].w * a);
+      }
     }
   }
   smax[w][lane] = m;
@@ -189,43 +199,51 @@ scale_w_u8_kernel(const float* __restrict__ G, int64_t ldg, int64_t n, const dou
                   float* __restrict__ W32, int64_t ldw, uint8_t* __restrict__ Wt, int64_t ldk,
                   int64_t plane_stride, int digits, float* __restrict__ cs) {
   __shared__ __align__(16) unsigned int tile[kSwCols][kSwLd];
-  __shared__ double sa[kSwRows], sb[kSwCols], sinv[kSwCols];
+  __shared__ float sa[kSwRows], sb[kSwCols], sinv[kSwCols];
   const int64_t j0 = (int64_t)blockIdx.x * kSwCols, i0 = (int64_t)blockIdx.y * kSwRows;
   if (threadIdx.x < kSwRows) {
     const int64_t i = i0 + threadIdx.x;
-    sa[threadIdx.x] = i < n ? inv_a[i] : 0.0;
+    sa[threadIdx.x] = i < n ? (float)inv_a[i] : 0.f;
   } else if (threadIdx.x < kSwRows + kSwCols) {
     const int t = threadIdx.x - kSwRows;
     const int64_t j = j0 + t;
-    const double b = j < n ? inv_b[j] : 1.0;
-    // s_j = 2^(e+1) with 2^e <= cmax < 2^(e+1) (1.0 for an all-zero column); 1 ulp of head-room covers the
-    // fp32 evaluation of the maximum
-    double s = 1.0;
+    const float b = j < n ? (float)inv_b[j] : 1.f;
+    // s_j = 2^e, the power of two strictly above the column maximum (1.0 for an all-zero column); 1 ulp of
+    // head-room covers the rounding of the maximum.  sinv = 256^digits / s_j is a power of two: the scaling below
+    // is exact.
+    int e = 0;
     if (j < n) {
-      const float cm = __uint_as_float(cmax_bits[j]) * (float)b * 1.000001f;
-      if (cm > 0.f) { int e; frexp((double)cm, &e); s = ldexp(1.0, e); }
-      if (blockIdx.y == 0 && cs) cs[j] = (float)ldexp(s, -8 * digits);
+      const float cm = __uint_as_float(cmax_bits[j]) * b * 1.000001f;
+      if (cm > 0.f) frexpf(cm, &e);
+      if (blockIdx.y == 0 && cs) cs[j] = ldexpf(1.f, e - 8 * digits);
     }
     sb[t] = b;
-    sinv[t] = ldexp(1.0 / s, 8 * digits);
+    sinv[t] = ldexpf(1.f, 8 * digits - e);
   }
   __syncthreads();
-  const double qmax = ldexp(1.0, 8 * digits) - 1.0;
+  // fp32 arithmetic: W = G * (1/k_i^(1-l)) * (1/k_j^l) carries <= 4 roundings (2.4e-7 relative, the two factors
+  // come from float64 pow) — the same W the fp32 output holds; the digits then represent that fp32 value to
+  // 2^-(8 digits) of the column maximum (cvt.rni saturates at 2^32 - 1).
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 columns x 4 row lanes
   const int64_t j = j0 + tx;
-  const double bj = sb[tx], sj = sinv[tx];
-#pragma unroll 8
-  for (int r = ty; r < kSwRows; r += 4) {
-    const int64_t i = i0 + r;
-    unsigned int qi = 0u;
-    if (i < n && j < n) {
-      const double w = (double)__ldg(G + i * ldg + j) * sa[r] * bj;
-      if (W32) W32[i * ldw + j] = (float)w;
-      double q = rint(w * sj);
-      q = q < 0.0 ? 0.0 : (q > qmax ? qmax : q);
-      qi = (unsigned int)q;
+  const float bj = sb[tx], sj = sinv[tx];
+  const float qmaxf = digits >= 4 ? 4294967040.f : ldexpf(1.f, 8 * digits) - 1.f;
+#pragma unroll 1
+  for (int r0 = ty; r0 < kSwRows; r0 += 32) {
+    float g[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int64_t i = i0 + r0 + 4 * u;
+      g[u] = (i < n && j < n) ? __ldg(G + i * ldg + j) : 0.f;
     }
-    tile[tx][r] = qi;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int r = r0 + 4 * u;
+      const int64_t i = i0 + r;
+      const float w = g[u] * sa[r] * bj;
+      if (W32 && i < n && j < n) W32[i * ldw + j] = w;
+      tile[tx][r] = __float2uint_rn(fminf(w * sj, qmaxf));
+    }
   }
   __syncthreads();
   // thread -> (column c, group g of four source items): lanes run over g, so a warp stores 128 contiguous bytes
