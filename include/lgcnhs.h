@@ -182,6 +182,40 @@ int lgc_score_topk(const float* Xu, const float* Xi, int64_t u0, int64_t u1, int
                    int32_t dim, const int32_t* seen_ptr, const int32_t* seen_idx, float fill,
                    int32_t exclude_seen, const float* mul, int64_t ldmul, int32_t k,
                    int64_t* out_idx, float* out_val, lgc_stream_t stream);
+/* ------------------------------------------------------------------------------------
+ * (N3) Structured negative sampling for BPR.  Replaces
+ * torch_geometric.utils.structured_negative_sampling as used by sampleMiniBatch
+ * (model/LightGCN/loss.py:46-70) and calValLoss (evaluation.py:72): for every requested edge
+ * (u, pos) draw neg uniformly from [0, num_nodes) until (u, neg) is not a positive pair (and
+ * neg != u when forbid_self).  rows (may be null = all edges) selects the edges; pos_ptr/pos_idx
+ * is the CSR of positive items per user (ascending).  *status (device int, zeroed by the caller)
+ * becomes non-zero on an out-of-range row / user id.  Counter-based generator: same seed, same
+ * triplets.
+ * ---------------------------------------------------------------------------------- */
+int lgc_negative_sample(const int64_t* edge_u, const int64_t* edge_p, int64_t n_edges,
+                        const int64_t* rows, int64_t n_out, const int32_t* pos_ptr,
+                        const int32_t* pos_idx, int64_t n_users, int64_t num_nodes,
+                        int32_t forbid_self, uint64_t seed, int64_t* out_u, int64_t* out_p,
+                        int64_t* out_n, int32_t* status, lgc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * (N1) The six evaluation metrics of a set of top-k lists, on the device.  Replaces
+ * metrics/accurate.py:11-102 (Precision / Recall / NDCG: per-user `item in items` loops) and the
+ * O(U^2) / O(U k^2 U) Python loops of metrics/diversity.py:15-115 (Hamming distance, intra-list
+ * similarity) by their closed forms:
+ *   out6[0] = sum_u hits_u            out6[1] = sum_u hits_u / |pos_u|      out6[2] = sum_u dcg_u / idcg
+ *   out6[3] = users with >= 1 positive item (the keys of user_pos_items_dict)
+ *   out6[4] = sum_i c_i (c_i - 1),  c_i = lists containing item i   (H = 1 - out6[4] / (U (U-1) k))
+ *   out6[5] = sum_u sum_{a != b in L_u} C[a,b] / sqrt(k_a k_b)       (I = out6[5] / (U k (k-1)))
+ *   rec int64 (n_users, k) row-major; pos_ptr/pos_idx: CSR of relevant items, ascending per row
+ *   (may be null: [0..3] stay 0); Cmat fp32 (n_items, ldc) = A^T A and item_deg int32[n_items]
+ *   (may both be null: [5] stays 0).  scratch: lgc_metrics_scratch_bytes(n_items), 16-byte aligned.
+ * ---------------------------------------------------------------------------------- */
+int64_t lgc_metrics_scratch_bytes(int64_t n_items);
+int lgc_metrics_topk(const int64_t* rec, int64_t n_users, int32_t k, int64_t n_items,
+                     const int32_t* pos_ptr, const int32_t* pos_idx, const float* Cmat, int64_t ldc,
+                     const int32_t* item_deg, double* out6, void* scratch, lgc_stream_t stream);
+
 /* CSR (rowptr, column ids) -> bit-packed mask with the given row stride; mask zero-filled by
  * the caller, (n_rows * stride_bits + 31) / 32 words. */
 int lgc_mask_from_csr(const int32_t* ptr, const int32_t* idx, int64_t n_rows, int64_t n_cols,

@@ -1,0 +1,57 @@
+"""Device implementations behind the drop-in metrics modules.
+
+The reference evaluates every set of top-k lists with per-user Python membership loops
+(/root/reference/metrics/accurate.py:27-35, 74-79), an O(U^2) pair loop with a string-keyed memo
+(/root/reference/metrics/diversity.py:31-57) and O(U k^2) length-U dot products (:88-108).  Here the lists,
+the relevant-item CSR and the interaction list go to the device once and lgc_metrics_topk returns the six sums;
+the co-occurrence matrix C = A^T A is an exact int8 tensor-core GEMM."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+def _dev() -> torch.device:
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def csr_from_lists(user_items: dict, n_users: int, dev: torch.device):
+    """dict{uid: [iid, ...]} -> int32 CSR over all users, items ascending per row, duplicates KEPT (the reference
+    divides by len(items), accurate.py:33)."""
+    uids = np.fromiter(user_items.keys(), dtype=np.int64, count=len(user_items))
+    lens = np.fromiter((len(v) for v in user_items.values()), dtype=np.int64, count=uids.size)
+    flat = np.concatenate([np.asarray(v, dtype=np.int64) for v in user_items.values()] or [np.empty(0, np.int64)])
+    rows = np.repeat(uids, lens)
+    order = np.lexsort((flat, rows))
+    cnt = np.bincount(rows, minlength=n_users)
+    ptr = np.zeros(n_users + 1, dtype=np.int64)
+    np.cumsum(cnt, out=ptr[1:])
+    return (torch.from_numpy(ptr.astype(np.int32)).to(dev), torch.from_numpy(flat[order].astype(np.int32)).to(dev))
+
+
+def accuracy_device(user_pos_items_dict: dict, recommendations: torch.Tensor, k: int) -> tuple:
+    dev = _dev()
+    rec = recommendations.detach().to(dev).long().contiguous()
+    U = int(rec.shape[0])
+    n_items = int(max(int(rec.max()) + 1, max((max(v) for v in user_pos_items_dict.values() if len(v)), default=0) + 1))
+    pos = csr_from_lists(user_pos_items_dict, U, dev)
+    sums = ops.topk_metrics(rec[:, :k].contiguous(), n_items, pos).cpu().tolist()
+    m = ops.metrics_from_sums(sums, U, k)
+    return m["precision"], m["recall"], m["f1"], m["ndcg"]
+
+
+def diversity_device(recommendations: torch.Tensor, item_degree_dict: dict, interaction_mat: np.ndarray, k: int) -> tuple:
+    dev = _dev()
+    rec = recommendations.detach().to(dev).long().contiguous()
+    U, M = int(interaction_mat.shape[0]), int(interaction_mat.shape[1])
+    u, i = np.nonzero(interaction_mat)
+    eng = ops.SpreadingEngine(U, M, torch.from_numpy(u).to(dev), torch.from_numpy(i).to(dev))
+    deg = np.zeros(M, dtype=np.int32)
+    for it, c in item_degree_dict.items():
+        if 0 <= int(it) < M:
+            deg[int(it)] = int(c)
+    sums = ops.topk_metrics(rec, M, None, eng.cooccurrence(), torch.from_numpy(deg).to(dev)).cpu().tolist()
+    m = ops.metrics_from_sums(sums, int(rec.shape[0]), k)
+    return m["H"], m["I"]

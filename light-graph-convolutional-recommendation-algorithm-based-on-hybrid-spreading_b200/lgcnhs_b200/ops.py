@@ -278,6 +278,35 @@ def topk_rows(S: torch.Tensor, k: int, excl: Optional[ExclusionMask] = None, row
     return idx, val
 
 
+def topk_metrics(rec: torch.Tensor, n_items: int, pos: Optional[tuple] = None, cooc: Optional[torch.Tensor] = None,
+                 item_deg: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Raw sums of the six metrics of the (U, k) lists `rec` as a float64[6] DEVICE tensor (see lgc_metrics_topk);
+    `metrics_from_sums` turns them into the reference's rounded numbers."""
+    rec = _req(rec, torch.int64, "rec")
+    U, k = int(rec.shape[0]), int(rec.shape[1])
+    if out is None:
+        out = torch.empty(6, dtype=torch.float64, device=rec.device)
+    pp, pi = (None, None) if pos is None else pos
+    if cooc is not None and (cooc.dtype != torch.float32 or cooc.stride(1) != 1 or cooc.shape[0] != n_items):
+        raise LgcnhsError("topk_metrics: cooc must be the fp32 (n_items, n_items) matrix A^T A")
+    scratch = torch.empty(int(lib().lgc_metrics_scratch_bytes(n_items)), dtype=torch.uint8, device=rec.device)
+    check(lib().lgc_metrics_topk(_ptr(rec), U, k, int(n_items), _ptr(pp), _ptr(pi), _ptr(cooc),
+                                 int(cooc.stride(0)) if cooc is not None else 0, _ptr(item_deg), _ptr(out), _ptr(scratch),
+                                 _stream()), "metrics_topk")
+    return out
+
+
+def metrics_from_sums(sums, n_users: int, k: int) -> dict:
+    """float64[6] sums (host) -> the reference's six numbers, rounded to 5 decimals like metrics/*.py."""
+    s = [float(x) for x in sums]
+    n = max(s[3], 1.0)
+    precision, recall, ndcg = round(s[0] / n / k, 5), round(s[1] / n, 5), round(s[2] / n, 5)
+    f1 = round(2 * precision * recall / (precision + recall), 5) if precision + recall > 0 else float("nan")
+    H = round(1.0 - s[4] / (n_users * (n_users - 1) * k), 5) if n_users > 1 else float("nan")
+    I = round(s[5] / (n_users * k * (k - 1)), 5) if k > 1 else float("nan")
+    return {"precision": precision, "recall": recall, "f1": f1, "ndcg": ndcg, "H": H, "I": I}
+
+
 def seen_csr(users: torch.Tensor, items: torch.Tensor, n_users: int, n_items: int):
     """(user, item) pairs -> deduplicated int32 CSR (rowptr, item ids ascending) on device."""
     key = torch.unique(users.to(torch.int64) * n_items + items.to(torch.int64))
@@ -364,6 +393,7 @@ class SpreadingEngine:
             check(L.hs_pack_a(_ptr(users), _ptr(items), self.nnz, U, M, _ptr(self.A), self.ldM, _stream()), "pack_a")
             self.col_scale = None
         self.G: Optional[torch.Tensor] = None
+        self.C: Optional[torch.Tensor] = None
         self.Wt: Optional[torch.Tensor] = None
 
     def excl_items(self, u: int) -> torch.Tensor:
@@ -407,6 +437,32 @@ class SpreadingEngine:
         if item_range is None:
             self.G = G
         return G
+
+    def cooccurrence(self, operands=None) -> torch.Tensor:
+        """C = A^T A (common-preference counts, metrics/diversity.py:104) — both operands 0/1, exact int32
+        accumulation on the tensor cores; (M, M) fp32 holding integers."""
+        if self.C is None:
+            At = (self.pack_g_operands()[0] if operands is None else operands[0])
+            self.C = gemm_planes(1, At, At.unsqueeze(0), self.M, self.M, self.U)
+        return self.C
+
+    def sweep(self, lambdas, k: int, test_pos: Optional[tuple] = None, filtered: bool = True,
+              gscore: Optional[torch.Tensor] = None, diversity: bool = True):
+        """The findLambda.py:83-116 loop on the device: G once, then per lambda  HybridS -> A.W [-> * gscore] ->
+        filtered top-k -> six metric sums, with no host round trip inside the loop.  Returns (sums float64
+        (n_lambda, 6) on the HOST after ONE device->host copy, list of per-lambda metric dicts)."""
+        if self.G is None:
+            self.general_w()
+        cooc = self.cooccurrence() if diversity else None
+        deg = self.ki if diversity else None
+        lambdas = [float(x) for x in lambdas]
+        sums = torch.zeros((len(lambdas), 6), dtype=torch.float64, device=self.dev)
+        F = torch.empty((self.U, _pad(self.M, 4)), dtype=torch.float32, device=self.dev)[:, : self.M]
+        for n, lam in enumerate(lambdas):
+            idx, _ = self.recommend(lam, k, filtered=filtered, gscore=gscore, F_out=F)
+            topk_metrics(idx, self.M, test_pos, cooc, deg, out=sums[n])
+        host = sums.cpu()
+        return host, [metrics_from_sums(host[n].tolist(), self.U, k) for n in range(len(lambdas))]
 
     def scale(self, lam: float, G: Optional[torch.Tensor] = None, want_w32: bool = False):
         """W = HybridS(A, G, lambda) (model/SpreadMethod/model.py:63-85) -> operand planes of W^T (+ fp32 W)."""

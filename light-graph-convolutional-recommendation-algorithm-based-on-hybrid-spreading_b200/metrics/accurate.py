@@ -48,6 +48,9 @@ def calNDCG(user_pos_items_dict: dict, recommendations: torch.Tensor, k: int) ->
 
 
 def getAccurateMetrics(user_pos_items_dict: dict, recommendations: torch.Tensor, k: int) -> tuple:
+    if torch.cuda.is_available() and len(user_pos_items_dict):
+        from lgcnhs_b200.metrics_device import accuracy_device   # lgc_metrics_topk: one warp per user
+        return accuracy_device(user_pos_items_dict, recommendations, k)
     precision, recall = calPrecisionAndRecall(user_pos_items_dict, recommendations, k)
     f1 = calF1Score(precision, recall)
     ndcg = calNDCG(user_pos_items_dict, recommendations, k)

@@ -51,6 +51,10 @@ def calInternalSimilarity(recommendations: torch.Tensor, item_degree_dict: dict,
 
 def getDiversityMetrics(recommendations: torch.Tensor, item_degree_dict: dict,
                         interaction_mat: np.ndarray, k: int) -> tuple:
+    if torch.cuda.is_available():
+        # device path (lgc_metrics_topk): item histogram + exact int8 tensor-core co-occurrence GEMM
+        from lgcnhs_b200.metrics_device import diversity_device
+        return diversity_device(recommendations, item_degree_dict, interaction_mat, k)
     H = calHammingDistance(recommendations, k)
     I = calInternalSimilarity(recommendations, item_degree_dict, interaction_mat, k)
     return H, I
