@@ -139,6 +139,15 @@ int lgc_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
                   int64_t n, float lr, float beta1, float beta2, float eps, float bc1,
                   float bc2_sqrt, lgc_stream_t stream);
 
+/* Device-resident variant for CUDA-graph capture of a whole training step: lgc_adam_hyper_step
+ * increments *step_dev and writes hyper_dev = {lr / (1 - beta1^step), sqrt(1 - beta2^step)};
+ * lgc_adam_step_dev reads those two scalars instead of host arguments. */
+int lgc_adam_hyper_step(int64_t* step_dev, const float* lr_dev, float beta1, float beta2,
+                        float* hyper_dev, lgc_stream_t stream);
+int lgc_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                      float beta1, float beta2, float eps, const float* hyper_dev,
+                      lgc_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * (P8) score = Xu . Xi^T  (+ optional seen-pair fill), materialised for a block of
  * users.  Replaces torch.matmul(user_embedding, item_embedding.T) and

@@ -152,7 +152,12 @@ static int launch_bpr(const BprPtrs& P, int dim, int64_t batch, float eps, float
 __global__ void adam_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
                             float4* __restrict__ v, int64_t n4, float* __restrict__ pt,
                             const float* __restrict__ gt, float* __restrict__ mt, float* __restrict__ vt,
-                            int tail, float beta1, float beta2, float eps, float step_size, float bc2_sqrt) {
+                            int tail, float beta1, float beta2, float eps, float step_size, float bc2_sqrt,
+                            const float* __restrict__ hyper) {
+  if (hyper) {  // step-dependent scalars kept on the device, so the whole step can live in a CUDA graph
+    step_size = hyper[0];
+    bc2_sqrt = hyper[1];
+  }
   auto upd = [&](float& pp, float gg, float& mm, float& vv) {
     mm = mm + (gg - mm) * (1.f - beta1);          // exp_avg.lerp_(grad, 1-beta1)
     vv = vv * beta2 + (1.f - beta2) * gg * gg;    // exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2)
@@ -172,6 +177,17 @@ __global__ void adam_kernel(float4* __restrict__ p, const float4* __restrict__ g
     upd(pp, gt[i], mm, vv);
     pt[i] = pp; mt[i] = mm; vt[i] = vv;
   }
+}
+
+// ++step; hyper = {lr / (1 - beta1^step), sqrt(1 - beta2^step)}  — torch.optim.Adam's bias corrections
+// (float64 like the Python side of torch's single-tensor path, rounded once to fp32)
+__global__ void adam_hyper_kernel(long long* __restrict__ step, const float* __restrict__ lr, double beta1, double beta2,
+                                  float* __restrict__ hyper) {
+  const long long t = *step + 1;
+  *step = t;
+  const float bc1 = (float)(1.0 - pow(beta1, (double)t));
+  hyper[0] = lr[0] / bc1;
+  hyper[1] = (float)sqrt(1.0 - pow(beta2, (double)t));
 }
 
 }  // namespace lgc
@@ -231,7 +247,32 @@ extern "C" int lgc_adam_step(float* param, const float* grad, float* exp_avg, fl
   if (grid > cap) grid = cap;
   adam_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
       (float4*)param, (const float4*)grad, (float4*)exp_avg, (float4*)exp_avg_sq, n4, param + n4 * 4,
-      grad + n4 * 4, exp_avg + n4 * 4, exp_avg_sq + n4 * 4, tail, beta1, beta2, eps, lr / bc1, bc2_sqrt);
+      grad + n4 * 4, exp_avg + n4 * 4, exp_avg_sq + n4 * 4, tail, beta1, beta2, eps, lr / bc1, bc2_sqrt, nullptr);
+  LGC_LAUNCH_CHECK("adam_kernel");
+  return LGC_OK;
+}
+
+extern "C" int lgc_adam_hyper_step(int64_t* step_dev, const float* lr_dev, float beta1, float beta2, float* hyper_dev,
+                                   lgc_stream_t stream) {
+  LGC_REQUIRE(step_dev && lr_dev && hyper_dev, "adam hyper: null pointer");
+  adam_hyper_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((long long*)step_dev, lr_dev, (double)beta1, (double)beta2, hyper_dev);
+  LGC_LAUNCH_CHECK("adam_hyper_kernel");
+  return LGC_OK;
+}
+
+extern "C" int lgc_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                 float beta1, float beta2, float eps, const float* hyper_dev, lgc_stream_t stream) {
+  LGC_REQUIRE(param && grad && exp_avg && exp_avg_sq && hyper_dev && n > 0, "adam: null pointer / empty");
+  LGC_REQUIRE((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0,
+              "adam: buffers must be 16-byte aligned");
+  const int64_t n4 = n / 4;
+  const int tail = (int)(n - n4 * 4);
+  int64_t grid = ceil_div(n4 > 0 ? n4 : 1, 256);
+  const int64_t cap = (int64_t)num_sms() * 16;
+  if (grid > cap) grid = cap;
+  adam_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+      (float4*)param, (const float4*)grad, (float4*)exp_avg, (float4*)exp_avg_sq, n4, param + n4 * 4,
+      grad + n4 * 4, exp_avg + n4 * 4, exp_avg_sq + n4 * 4, tail, beta1, beta2, eps, 0.f, 1.f, hyper_dev);
   LGC_LAUNCH_CHECK("adam_kernel");
   return LGC_OK;
 }

@@ -36,6 +36,8 @@ _SIGS = {
     "lgc_bpr_fwd_bwd": (C.c_int, [_p, _p, _i64, _i64, _i32, _p, _p, _p, _i64, _f32, _f32, _p, _p, _p, _p, _p]),
     "lgc_bpr_rows": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i32, _f32, _f32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "lgc_adam_step": (C.c_int, [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _p]),
+    "lgc_adam_hyper_step": (C.c_int, [_p, _p, _f32, _f32, _p, _p]),
+    "lgc_adam_step_dev": (C.c_int, [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _p, _p]),
     "lgc_score_block": (C.c_int, [_p, _p, _i64, _i64, _i64, _i32, _p, _p, _f32, _p, _i64, _p]),
     "lgc_topk_rows": (C.c_int, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i32, _p, _p, _p]),
     "lgc_score_topk": (C.c_int, [_p, _p, _i64, _i64, _i64, _i32, _p, _p, _f32, _i32, _p, _i64, _i32, _p, _p, _p]),

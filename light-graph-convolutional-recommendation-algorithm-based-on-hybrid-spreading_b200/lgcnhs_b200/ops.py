@@ -207,6 +207,20 @@ def adam_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, ex
                               float(beta1), float(beta2), float(eps), float(bc1), float(bc2_sqrt), _stream()), "adam")
 
 
+def adam_hyper_step(step_dev: torch.Tensor, lr_dev: torch.Tensor, beta1: float, beta2: float, hyper_dev: torch.Tensor) -> None:
+    """++step (device int64) and hyper = {lr / (1 - beta1^step), sqrt(1 - beta2^step)} on the device."""
+    check(lib().lgc_adam_hyper_step(_ptr(step_dev), _ptr(lr_dev), float(beta1), float(beta2), _ptr(hyper_dev), _stream()),
+          "adam hyper")
+
+
+def adam_step_dev(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, beta1: float,
+                  beta2: float, eps: float, hyper_dev: torch.Tensor) -> None:
+    for t, nm in ((param, "param"), (grad, "grad"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        _req(t, torch.float32, nm)
+    check(lib().lgc_adam_step_dev(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), int(param.numel()), float(beta1),
+                                  float(beta2), float(eps), _ptr(hyper_dev), _stream()), "adam (device hyper)")
+
+
 # --------------------------------------------------------------------------------------------
 # (P8/S4) scores and top-k
 # --------------------------------------------------------------------------------------------
