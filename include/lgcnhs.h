@@ -59,7 +59,7 @@ void lgc_reset_launch_count(void);
  * (chunk_row/chunk_start, at most lgc_csr_max_chunks(nnz) of them) so that the SpMM can
  * split them over several CTAs; *n_chunks_host receives the count (one D2H sync).
  * ---------------------------------------------------------------------------------- */
-#define LGC_LONG_ROW 256   /* rows with more non-zeros than this go to the chunk path */
+#define LGC_LONG_ROW 256  /* rows with more non-zeros than this go to the chunk path */
 #define LGC_CHUNK 1024     /* non-zeros per long-row chunk (one CTA)                  */
 
 int64_t lgc_csr_max_chunks(int64_t nnz);
@@ -80,6 +80,12 @@ int lgc_csr_build(const int64_t* src, const int64_t* dst, int64_t nnz, int64_t n
  * `partial` is scratch of lgc_csr_max_chunks(nnz)*dim floats, `counters` is n_nodes
  * int32 that must be zero on entry (the kernel leaves them zero).
  * row_begin/row_end restrict the launch to a row range (multi-GPU row partition);
+ * row_order (may be null) lists the rows of that range in processing order, row_end - row_begin
+ * entries — longest first keeps the eight rows of a CTA alike and the last wave short;
+ * long_row (needs row_order; clamped to [LGC_LONG_ROW, 2048]): rows with up to this many
+ * non-zeros take the warp-per-row path — about 1e-4 x the launch's non-zeros is right on B200.
+ * A row's fp32 summation order depends on the path, so results are bit-reproducible for a given
+ * (row range, long_row) and may differ in the last bits between configurations;
  * chunk_begin/chunk_end = row_chunk_base[row_begin], row_chunk_base[row_end] are the
  * long-row chunks of that range ([0, n_chunks) for the whole graph).
  * ---------------------------------------------------------------------------------- */
@@ -87,11 +93,15 @@ int lgc_spmm_layer(const int32_t* rowptr, const int32_t* colidx, const float* va
                    const int32_t* chunk_row, const int32_t* chunk_start,
                    const int32_t* row_chunk_base, int32_t chunk_begin, int32_t chunk_end,
                    int64_t n_nodes, int32_t dim, int64_t row_begin, int64_t row_end,
-                   const float* X, const float* X0, float alpha, float beta, float* Y,
-                   float* partial, int32_t* counters, lgc_stream_t stream);
+                   const int32_t* row_order, int32_t long_row, const float* X, const float* X0,
+                   float alpha, float beta, float* Y, float* partial, int32_t* counters,
+                   lgc_stream_t stream);
 
 /* Tuning knob: independent 128-bit gathers in flight per lane for dim 64 (2, 4 or 8). */
 int lgc_spmm_config(int32_t unroll);
+/* Tuning knob: override of the per-call long_row for the launches that follow (in [LGC_LONG_ROW, 2048];
+ * 0 = use the per-call value).  The chunk lists always cover rows > LGC_LONG_ROW. */
+int lgc_spmm_long_row(int32_t long_row);
 
 /* K-layer forward with the uniform layer mean in Horner form
  *   S_0 = X0,  S_{l+1} = A_hat S_l + X0,  E = S_K / (K+1)
@@ -101,6 +111,7 @@ int lgc_propagate_mean(const int32_t* rowptr, const int32_t* colidx, const float
                        const int32_t* chunk_row, const int32_t* chunk_start,
                        const int32_t* row_chunk_base, int32_t n_chunks,
                        int64_t n_nodes, int32_t dim, int32_t n_layers,
+                       const int32_t* row_order /* n_nodes entries or null */, int32_t long_row,
                        const float* X0, float* E, float* tmp0, float* tmp1,
                        float* partial, int32_t* counters, lgc_stream_t stream);
 
@@ -191,6 +202,13 @@ int lgc_score_topk(const float* Xu, const float* Xi, int64_t u0, int64_t u1, int
                    int32_t dim, const int32_t* seen_ptr, const int32_t* seen_idx, float fill,
                    int32_t exclude_seen, const float* mul, int64_t ldmul, int32_t k,
                    int64_t* out_idx, float* out_val, lgc_stream_t stream);
+/* Device-side barrier over peer memory (replaces one NCCL all-reduce per propagation layer in the multi-GPU
+ * p2p mode).  Every rank owns local_flags[n_peers] in IPC-mapped memory, zero-initialised; the call publishes
+ * `epoch` into peer_flags_host[p][my_rank] for every p and returns (stream-ordered) once local_flags[q] >= epoch
+ * for all q.  Epochs must grow monotonically.  Launch it right after the layer's lgc_spmm_layer_bcast. */
+int lgc_peer_barrier(const int32_t* local_flags, int32_t* const* peer_flags_host, int32_t my_rank,
+                     int32_t n_peers, int32_t epoch, lgc_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * (N3) Structured negative sampling for BPR.  Replaces
  * torch_geometric.utils.structured_negative_sampling as used by sampleMiniBatch
@@ -325,7 +343,8 @@ int lgc_spmm_layer_bcast(const int32_t* rowptr, const int32_t* colidx, const flo
                          const int32_t* chunk_row, const int32_t* chunk_start,
                          const int32_t* row_chunk_base, int32_t chunk_begin,
                          int32_t chunk_end, int64_t n_nodes,
-                         int32_t dim, int64_t row_begin, int64_t row_end, const float* X,
+                         int32_t dim, int64_t row_begin, int64_t row_end,
+                         const int32_t* row_order, int32_t long_row, const float* X,
                          const float* X0, float alpha, float beta,
                          float* const* peer_Y_host, int32_t n_peers, float* partial,
                          int32_t* counters, lgc_stream_t stream);

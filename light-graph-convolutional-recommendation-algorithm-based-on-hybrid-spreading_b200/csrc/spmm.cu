@@ -27,6 +27,7 @@ constexpr int kWarpsPerBlock = 8;
 constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr int kMaxPeers = 8;
 
+static int g_spmm_long_row = 0;  // override of the per-call warp-per-row threshold (lgc_spmm_long_row); 0 = none
 static int g_spmm_unroll = 0;  // gathers in flight per lane for DIM=64; 0 = choose by grid size (lgc_spmm_config)
 
 struct PeerPtrs {
@@ -115,19 +116,22 @@ spmm_layer_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
                   const float* __restrict__ val, const int32_t* __restrict__ chunk_row,
                   const int32_t* __restrict__ chunk_start, const int32_t* __restrict__ row_chunk_base,
                   int chunk_begin, int n_chunk_blocks, int row_begin, int row_end,
+                  const int32_t* __restrict__ row_order,
                   const float* __restrict__ X, const float* __restrict__ X0, float alpha, float beta,
                   float* __restrict__ Y, PeerPtrs peers, float* __restrict__ partial,
-                  int32_t* __restrict__ counters, int n_peers_rt) {
+                  int32_t* __restrict__ counters, int long_row) {
   constexpr int LPR = DIM / 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  (void)n_peers_rt;
 
   if ((int)blockIdx.x >= n_chunk_blocks) {
     // ---------------- short rows: one warp per row ----------------
-    const int row = row_begin + ((int)blockIdx.x - n_chunk_blocks) * kWarpsPerBlock + warp;
-    if (row >= row_end) return;
+    // row_order (optional): the rows of [row_begin, row_end) longest first, so that the eight rows of a CTA have
+    // similar lengths (its slot is not held by one straggler) and the last wave consists of the shortest rows
+    const int slot = row_begin + ((int)blockIdx.x - n_chunk_blocks) * kWarpsPerBlock + warp;
+    if (slot >= row_end) return;
+    const int row = row_order ? __ldg(row_order + (slot - row_begin)) : slot;
     const int start = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
-    if (end - start > LGC_LONG_ROW) return;  // handled by the chunk CTAs
+    if (end - start > long_row) return;  // handled by the chunk CTAs
     float4 acc = warp_gather_sum<DIM, UN>(colidx, val, X, start, end, lane);
     if (lane < LPR) {
       const size_t off = (size_t)row * DIM + lane * 4;
@@ -151,6 +155,7 @@ spmm_layer_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
   const int row = __ldg(chunk_row + chunk);
   const int cstart = __ldg(chunk_start + chunk);
   const int rstart = __ldg(rowptr + row), rend = __ldg(rowptr + row + 1);
+  if (rend - rstart <= long_row) return;  // this launch handles the row in the warp-per-row path
   const int cend = min(cstart + LGC_CHUNK, rend);
   constexpr int PER_WARP = LGC_CHUNK / kWarpsPerBlock;
   const int wstart = min(cstart + warp * PER_WARP, cend), wend = min(wstart + PER_WARP, cend);
@@ -197,13 +202,42 @@ spmm_layer_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
   }
 }
 
+// Device-side barrier over peer memory, replacing one NCCL all-reduce per layer in the multi-GPU p2p mode.
+// Launched on the stream right after the layer's SpMM: the kernel boundary has completed that rank's row stores
+// (local and peer); lane p then publishes `epoch` into peer p's flag array (release, system scope) and waits until
+// every peer has published it into ours (acquire).  Epochs only grow, so the flags are never reset.  One rank per
+// GPU: the kernels that wait on each other always run concurrently.
+struct PeerFlags {
+  int32_t* f[kMaxPeers];
+};
+
+__global__ void peer_barrier_kernel(const int32_t* __restrict__ local_flags, PeerFlags peers, int my_rank, int n_peers,
+                                    int32_t epoch) {
+  const int p = threadIdx.x;
+  if (p < n_peers) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(peers.f[p] + my_rank), "r"(epoch) : "memory");
+    const long long t0 = clock64();
+    int32_t v;
+    do {
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(local_flags + p) : "memory");
+      if (v >= epoch) break;
+      if (clock64() - t0 > 20000000000ll) {  // ~10 s: a missing peer must trap instead of hanging the GPU
+        printf("lgcnhs peer barrier: rank %d never saw peer %d reach epoch %d\n", my_rank, p, epoch);
+        __trap();
+      }
+      __nanosleep(32);
+    } while (true);
+  }
+}
+
 template <int NPEER>
 static int launch_spmm(const int32_t* rowptr, const int32_t* colidx, const float* val,
                        const int32_t* chunk_row, const int32_t* chunk_start,
                        const int32_t* row_chunk_base, int chunk_begin, int chunk_end,
-                       int64_t row_begin, int64_t row_end, int dim, const float* X, const float* X0,
-                       float alpha, float beta, float* Y, const PeerPtrs& peers, float* partial,
-                       int32_t* counters, cudaStream_t stream) {
+                       int64_t row_begin, int64_t row_end, const int32_t* row_order, int long_row_arg, int dim,
+                       const float* X, const float* X0, float alpha, float beta, float* Y, const PeerPtrs& peers,
+                       float* partial, int32_t* counters, cudaStream_t stream) {
   const int n_chunk_blocks = chunk_end - chunk_begin;
   const int64_t n_rows = row_end - row_begin;
   const int64_t grid = n_chunk_blocks + ceil_div(n_rows, kWarpsPerBlock);
@@ -211,7 +245,16 @@ static int launch_spmm(const int32_t* rowptr, const int32_t* colidx, const float
 #define LGC_SPMM_LAUNCH(D, UNR)                                                                   \
   spmm_layer_kernel<D, NPEER, UNR><<<(unsigned)grid, kThreads, 0, stream>>>(                      \
       rowptr, colidx, val, chunk_row, chunk_start, row_chunk_base, chunk_begin, n_chunk_blocks,   \
-      (int)row_begin, (int)row_end, X, X0, alpha, beta, Y, peers, partial, counters, NPEER)
+      (int)row_begin, (int)row_end, row_order, X, X0, alpha, beta, Y, peers, partial, counters, long_row)
+  // Rows of LGC_LONG_ROW < nnz <= long_row take the warp-per-row path in this launch: it is cheaper than chunk
+  // partials + ticket + re-read (ML-20M layer: 680 -> 525 us at long_row 1024), but a lone warp streams only ~40
+  // non-zeros per microsecond, so only launches with enough work hide such rows, and they must be issued first
+  // (row_order).  The caller sizes long_row to the launch (about 1e-4 x its non-zeros, lgcnhs_b200/ops.py).
+  // A row's fp32 summation order depends on the path it takes, so results are reproducible for a given launch
+  // configuration and may differ in the last bits between configurations (1 GPU vs a row partition).
+  int long_row = g_spmm_long_row ? g_spmm_long_row : long_row_arg;
+  if (long_row < LGC_LONG_ROW || !row_order) long_row = LGC_LONG_ROW;
+  if (long_row > 2048) long_row = 2048;
   switch (dim) {
     case 32: LGC_SPMM_LAUNCH(32, 4); break;
     case 64:
@@ -259,28 +302,36 @@ extern "C" int lgc_spmm_config(int32_t unroll) {
   return LGC_OK;
 }
 
+extern "C" int lgc_spmm_long_row(int32_t long_row) {
+  LGC_REQUIRE(long_row == 0 || (long_row >= LGC_LONG_ROW && long_row <= 2048),
+              "spmm long_row: 0 (per-call value) or in [LGC_LONG_ROW, 2048]");
+  g_spmm_long_row = long_row;
+  return LGC_OK;
+}
+
 extern "C" int lgc_spmm_layer(const int32_t* rowptr, const int32_t* colidx, const float* val,
                               const int32_t* chunk_row, const int32_t* chunk_start,
                               const int32_t* row_chunk_base, int32_t chunk_begin, int32_t chunk_end,
                               int64_t n_nodes, int32_t dim, int64_t row_begin, int64_t row_end,
-                              const float* X, const float* X0, float alpha, float beta, float* Y,
-                              float* partial, int32_t* counters, lgc_stream_t stream) {
+                              const int32_t* row_order, int32_t long_row, const float* X, const float* X0,
+                              float alpha, float beta, float* Y, float* partial, int32_t* counters,
+                              lgc_stream_t stream) {
   int rc = check_spmm_args(rowptr, colidx, val, chunk_row, chunk_start, row_chunk_base, chunk_begin,
                            chunk_end, n_nodes, row_begin, row_end, X, X0, beta, partial, counters);
   if (rc) return rc;
   LGC_REQUIRE(Y && ((uintptr_t)Y & 15) == 0, "spmm: Y null or misaligned");
   PeerPtrs none{};
   return launch_spmm<0>(rowptr, colidx, val, chunk_row, chunk_start, row_chunk_base, chunk_begin,
-                        chunk_end, row_begin, row_end, dim, X, X0, alpha, beta, Y, none, partial,
-                        counters, (cudaStream_t)stream);
+                        chunk_end, row_begin, row_end, row_order, long_row, dim, X, X0, alpha, beta, Y, none,
+                        partial, counters, (cudaStream_t)stream);
 }
 
 extern "C" int lgc_spmm_layer_bcast(const int32_t* rowptr, const int32_t* colidx, const float* val,
                                     const int32_t* chunk_row, const int32_t* chunk_start,
                                     const int32_t* row_chunk_base, int32_t chunk_begin,
                                     int32_t chunk_end, int64_t n_nodes, int32_t dim,
-                                    int64_t row_begin, int64_t row_end, const float* X,
-                                    const float* X0, float alpha, float beta,
+                                    int64_t row_begin, int64_t row_end, const int32_t* row_order,
+                                    int32_t long_row, const float* X, const float* X0, float alpha, float beta,
                                     float* const* peer_Y_host, int32_t n_peers, float* partial,
                                     int32_t* counters, lgc_stream_t stream) {
   int rc = check_spmm_args(rowptr, colidx, val, chunk_row, chunk_start, row_chunk_base, chunk_begin,
@@ -296,8 +347,8 @@ extern "C" int lgc_spmm_layer_bcast(const int32_t* rowptr, const int32_t* colidx
 #define LGC_BCAST(NP)                                                                              \
   case NP:                                                                                         \
     return launch_spmm<NP>(rowptr, colidx, val, chunk_row, chunk_start, row_chunk_base,            \
-                           chunk_begin, chunk_end, row_begin, row_end, dim, X, X0, alpha, beta,    \
-                           nullptr, peers, partial, counters, s)
+                           chunk_begin, chunk_end, row_begin, row_end, row_order, long_row, dim, X, X0, \
+                           alpha, beta, nullptr, peers, partial, counters, s)
   switch (n_peers) {
     LGC_BCAST(1); LGC_BCAST(2); LGC_BCAST(3); LGC_BCAST(4);
     LGC_BCAST(5); LGC_BCAST(6); LGC_BCAST(7); LGC_BCAST(8);
@@ -306,12 +357,27 @@ extern "C" int lgc_spmm_layer_bcast(const int32_t* rowptr, const int32_t* colidx
   return LGC_ERR_INVALID;
 }
 
+extern "C" int lgc_peer_barrier(const int32_t* local_flags, int32_t* const* peer_flags_host, int32_t my_rank,
+                                int32_t n_peers, int32_t epoch, lgc_stream_t stream) {
+  LGC_REQUIRE(local_flags && peer_flags_host, "peer barrier: null pointer");
+  LGC_REQUIRE(n_peers >= 1 && n_peers <= kMaxPeers && my_rank >= 0 && my_rank < n_peers && epoch > 0,
+              "peer barrier: bad rank / epoch");
+  PeerFlags pf{};
+  for (int p = 0; p < n_peers; ++p) {
+    LGC_REQUIRE(peer_flags_host[p], "peer barrier: null peer flag array");
+    pf.f[p] = peer_flags_host[p];
+  }
+  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(local_flags, pf, my_rank, n_peers, epoch);
+  LGC_LAUNCH_CHECK("peer_barrier_kernel");
+  return LGC_OK;
+}
+
 extern "C" int lgc_propagate_mean(const int32_t* rowptr, const int32_t* colidx, const float* val,
                                   const int32_t* chunk_row, const int32_t* chunk_start,
                                   const int32_t* row_chunk_base, int32_t n_chunks, int64_t n_nodes,
-                                  int32_t dim, int32_t n_layers, const float* X0, float* E,
-                                  float* tmp0, float* tmp1, float* partial, int32_t* counters,
-                                  lgc_stream_t stream) {
+                                  int32_t dim, int32_t n_layers, const int32_t* row_order, int32_t long_row,
+                                  const float* X0, float* E, float* tmp0, float* tmp1, float* partial,
+                                  int32_t* counters, lgc_stream_t stream) {
   LGC_REQUIRE(X0 && E && n_layers >= 0, "propagate_mean: bad arguments");
   if (n_layers == 0) {
     LGC_CUDA(cudaMemcpyAsync(E, X0, sizeof(float) * (size_t)n_nodes * dim, cudaMemcpyDeviceToDevice,
@@ -327,8 +393,8 @@ extern "C" int lgc_propagate_mean(const int32_t* rowptr, const int32_t* colidx, 
     float* out = last ? E : bufs[l & 1];
     const float alpha = last ? 1.0f / (float)(n_layers + 1) : 1.0f;
     int rc = lgc_spmm_layer(rowptr, colidx, val, chunk_row, chunk_start, row_chunk_base, 0, n_chunks,
-                            n_nodes, dim, 0, n_nodes, cur, X0, alpha, 1.0f, out, partial, counters,
-                            stream);
+                            n_nodes, dim, 0, n_nodes, row_order, long_row, cur, X0, alpha, 1.0f, out, partial,
+                            counters, stream);
     if (rc) return rc;
     cur = out;
   }

@@ -26,12 +26,14 @@ _SIGS = {
     "lgc_csr_max_chunks": (_i64, [_i64]),
     "lgc_csr_build_workspace_bytes": (C.c_int, [_i64, _i64, C.POINTER(_sz)]),
     "lgc_csr_build": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, C.POINTER(_i32), _p, _sz, _p]),
-    "lgc_spmm_layer": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i64, _i32, _i64, _i64, _p, _p, _f32, _f32,
+    "lgc_spmm_layer": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i64, _i32, _i64, _i64, _p, _i32, _p, _p, _f32, _f32,
                                  _p, _p, _p, _p]),
-    "lgc_spmm_layer_bcast": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i64, _i32, _i64, _i64, _p, _p, _f32,
+    "lgc_spmm_layer_bcast": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i64, _i32, _i64, _i64, _p, _i32, _p, _p, _f32,
                                        _f32, C.POINTER(_p), _i32, _p, _p, _p]),
+    "lgc_peer_barrier": (C.c_int, [_p, C.POINTER(_p), _i32, _i32, _i32, _p]),
     "lgc_spmm_config": (C.c_int, [_i32]),
-    "lgc_propagate_mean": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _p]),
+    "lgc_spmm_long_row": (C.c_int, [_i32]),
+    "lgc_propagate_mean": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i64, _i32, _i32, _p, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "lgc_bpr_scratch_floats": (_i64, [_i64]),
     "lgc_bpr_fwd_bwd": (C.c_int, [_p, _p, _i64, _i64, _i32, _p, _p, _p, _i64, _f32, _f32, _p, _p, _p, _p, _p]),
     "lgc_bpr_rows": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i32, _f32, _f32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),

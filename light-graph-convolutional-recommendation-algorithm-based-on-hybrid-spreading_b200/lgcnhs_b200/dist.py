@@ -3,9 +3,12 @@ barriers), rows of A_hat partitioned by non-zeros, per-layer exchange of the new
 
 The reference is single-process; this is the B200-native design of SURVEY.md
 §8(e).  Two exchange modes:
-  * "p2p"  (default): the all-gather is FUSED INTO THE SpMM — every finished row is stored into
-    all peers' replicas through CUDA-IPC-mapped pointers (NVLink stores issued by the kernel
-    that computed the row), followed by one tiny NCCL all-reduce as the layer barrier;
+  * "p2p"  (default): the all-gather is FUSED INTO THE SpMM — every finished row is stored into all peers'
+    replicas through CUDA-IPC-mapped pointers (NVLink stores issued by the kernel that computed the row) — and the
+    layer barrier is a one-warp kernel over epoch flags in peer memory (lgc_peer_barrier), so a K-layer call makes
+    no NCCL call at all;
+  * "p2p-nccl": same stores, one tiny NCCL all-reduce per layer as the barrier (the earlier design, kept for
+    comparison);
   * "nccl": compute locally, then one broadcast per rank (the library baseline).
 """
 from __future__ import annotations
@@ -67,23 +70,39 @@ def _ipc_import(blob: bytes) -> int:
 class RowPartitionedPropagation:
     """K-layer propagation + layer mean with the rows of A_hat split over the ranks."""
 
-    def __init__(self, edge_index: torch.Tensor, n_nodes: int, dim: int, mode: str = "p2p"):
+    def __init__(self, edge_index: torch.Tensor, n_nodes: int, dim: int, mode: str = "p2p",
+                 split: Optional[int] = None):
+        """split = n_users partitions the user rows and the item rows SEPARATELY (each rank owns one slice of
+        both): user rows gather from the small, popularity-skewed item table and item rows from the large user
+        table, so their cost per non-zero differs and a single nnz-balanced cut would leave the item-row ranks
+        behind."""
         assert dist.is_initialized(), "RowPartitionedPropagation needs an initialised process group"
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.mode = mode
         self.dev = edge_index.device
         self.n, self.dim = n_nodes, dim
         self.g = NormGraph(edge_index, n_nodes)
-        bounds = partition_rows_by_nnz(self.g.rowptr.cpu().numpy(), self.world)
-        self.bounds = [int(b) for b in bounds]
-        self.r0, self.r1 = self.bounds[self.rank], self.bounds[self.rank + 1]
-        self.chunks = self.g.chunk_range(self.r0, self.r1)
+        rowptr = self.g.rowptr.cpu().numpy()
+        # parts[r] = list of (row_begin, row_end) ranges owned by rank r
+        if split is None or split <= 0 or split >= n_nodes:
+            b = [int(x) for x in partition_rows_by_nnz(rowptr, self.world)]
+            self.parts = [[(b[r], b[r + 1])] for r in range(self.world)]
+        else:
+            bu = [int(x) for x in partition_rows_by_nnz(rowptr[: split + 1], self.world)]
+            bi = [int(x) + split for x in partition_rows_by_nnz(rowptr[split:] - rowptr[split], self.world)]
+            self.parts = [[(bu[r], bu[r + 1]), (bi[r], bi[r + 1])] for r in range(self.world)]
+        self.my_parts = [(a, b, self.g.chunk_range(a, b)) for a, b in self.parts[self.rank] if b > a]
+        self.r0, self.r1 = self.parts[self.rank][0]
         # replicated activations: two ping-pong layers + the result
         self.bufs = [torch.zeros((n_nodes, dim), dtype=torch.float32, device=self.dev) for _ in range(3)]
         self._flag = torch.zeros(1, dtype=torch.float32, device=self.dev)
         self.peer_ptrs: list[list[int]] = []
-        if mode == "p2p":
-            blobs = [_ipc_export(b) for b in self.bufs]
+        self.peer_flag_ptrs: list[int] = []
+        self.epoch = 0
+        if mode in ("p2p", "p2p-nccl"):
+            # epoch flags live in their own allocation (cudaIpc handles cover whole allocations)
+            self.flags = torch.zeros(64, dtype=torch.int32, device=self.dev)
+            blobs = [_ipc_export(b) for b in self.bufs] + [_ipc_export(self.flags)]
             gathered: list = [None] * self.world
             dist.all_gather_object(gathered, blobs)
             for bi in range(3):
@@ -91,6 +110,9 @@ class RowPartitionedPropagation:
                 for r in range(self.world):
                     ptrs.append(self.bufs[bi].data_ptr() if r == self.rank else _ipc_import(gathered[r][bi]))
                 self.peer_ptrs.append(ptrs)
+            for r in range(self.world):
+                self.peer_flag_ptrs.append(self.flags.data_ptr() if r == self.rank else _ipc_import(gathered[r][3]))
+        torch.cuda.synchronize()
         dist.barrier()
 
     def _layer_barrier(self):
@@ -106,15 +128,24 @@ class RowPartitionedPropagation:
             oi = 2 if last else (l & 1)
             alpha = 1.0 / (layers + 1) if last else 1.0
             if self.mode == "p2p":
-                g.spmm_bcast(cur, x0, alpha, 1.0, self.peer_ptrs[oi], self.r0, self.r1, self.chunks)
+                for a, b, ch in self.my_parts:
+                    g.spmm_bcast(cur, x0, alpha, 1.0, self.peer_ptrs[oi], a, b, ch)
+                self.epoch += 1
+                farr = (C.c_void_p * self.world)(*[C.c_void_p(p) for p in self.peer_flag_ptrs])
+                check(lib().lgc_peer_barrier(self.flags.data_ptr(), farr, self.rank, self.world, self.epoch,
+                                             torch.cuda.current_stream().cuda_stream), "peer barrier")
+            elif self.mode == "p2p-nccl":
+                for a, b, ch in self.my_parts:
+                    g.spmm_bcast(cur, x0, alpha, 1.0, self.peer_ptrs[oi], a, b, ch)
                 self._layer_barrier()
             else:
                 out = self.bufs[oi]
-                g.spmm(cur, x0, alpha, 1.0, out=out, row_begin=self.r0, row_end=self.r1, chunks=self.chunks)
+                for a, b, ch in self.my_parts:
+                    g.spmm(cur, x0, alpha, 1.0, out=out, row_begin=a, row_end=b, chunks=ch)
                 for r in range(self.world):
-                    a, b = self.bounds[r], self.bounds[r + 1]
-                    if b > a:
-                        dist.broadcast(out[a:b], src=r)
+                    for a, b in self.parts[r]:
+                        if b > a:
+                            dist.broadcast(out[a:b], src=r)
             cur = self.bufs[oi]
         return cur if layers > 0 else x0
 

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -78,6 +79,30 @@ class NormGraph:
         self.chunk_row = self.chunk_row[: max(self.n_chunks, 1)].clone()
         self.chunk_start = self.chunk_start[: max(self.n_chunks, 1)].clone()
         self._scratch: dict[int, tuple[torch.Tensor, torch.Tensor]] = {}
+        self._orders: dict[tuple[int, int], torch.Tensor] = {}
+        self._long_rows: dict[tuple[int, int], int] = {}
+        self.use_row_order = os.environ.get("LGCNHS_NO_ROW_ORDER", "0") != "1"
+
+    def row_order(self, row_begin: int = 0, row_end: Optional[int] = None) -> Optional[torch.Tensor]:
+        """Rows of [row_begin, row_end) longest first (int32), cached per range; None when disabled."""
+        if not self.use_row_order:
+            return None
+        row_end = self.n_nodes if row_end is None else row_end
+        key = (row_begin, row_end)
+        o = self._orders.get(key)
+        if o is None:
+            rp = self.rowptr[row_begin: row_end + 1].to(torch.int64)
+            o = (torch.argsort(rp[1:] - rp[:-1], descending=True, stable=True) + row_begin).to(torch.int32)
+            self._orders[key] = o
+            # warp-per-row threshold sized to the launch: a lone warp streams ~40 non-zeros per microsecond, so rows
+            # up to ~1e-4 x nnz(launch) hide inside the launch when issued first (tools/spmm_rows_probe.py, B200)
+            nnz = int(rp[-1] - rp[0])
+            t = 2 ** int(round(math.log2(max(1.0, nnz * 1e-4))))
+            self._long_rows[key] = int(min(2048, max(LONG_ROW, t)))
+        return o
+
+    def long_row(self, row_begin: int = 0, row_end: Optional[int] = None) -> int:
+        return self._long_rows.get((row_begin, self.n_nodes if row_end is None else row_end), LONG_ROW)
 
     def _scr(self, dim: int):
         s = self._scratch.get(dim)
@@ -112,8 +137,9 @@ class NormGraph:
         partial, counters = self._scr(dim)
         check(lib().lgc_spmm_layer(_ptr(self.rowptr), _ptr(self.colidx), _ptr(self.val), _ptr(self.chunk_row),
                                    _ptr(self.chunk_start), _ptr(self.row_chunk_base), cb, ce, n, dim, row_begin,
-                                   row_end, _ptr(X), _ptr(X0), float(alpha), float(beta), _ptr(out), _ptr(partial),
-                                   _ptr(counters), _stream()), "spmm layer")
+                                   row_end, _ptr(self.row_order(row_begin, row_end)), self.long_row(row_begin, row_end),
+                                   _ptr(X), _ptr(X0), float(alpha), float(beta), _ptr(out), _ptr(partial), _ptr(counters),
+                                   _stream()), "spmm layer")
         return out
 
     def spmm_bcast(self, X: torch.Tensor, X0: Optional[torch.Tensor], alpha: float, beta: float,
@@ -125,8 +151,9 @@ class NormGraph:
         arr = (C.c_void_p * len(peer_ptrs))(*[C.c_void_p(p) for p in peer_ptrs])
         check(lib().lgc_spmm_layer_bcast(_ptr(self.rowptr), _ptr(self.colidx), _ptr(self.val), _ptr(self.chunk_row),
                                          _ptr(self.chunk_start), _ptr(self.row_chunk_base), chunks[0], chunks[1], n,
-                                         dim, row_begin, row_end, _ptr(X), _ptr(X0), float(alpha), float(beta), arr,
-                                         len(peer_ptrs), _ptr(partial), _ptr(counters), _stream()),
+                                         dim, row_begin, row_end, _ptr(self.row_order(row_begin, row_end)),
+                                         self.long_row(row_begin, row_end), _ptr(X), _ptr(X0), float(alpha), float(beta),
+                                         arr, len(peer_ptrs), _ptr(partial), _ptr(counters), _stream()),
               "spmm layer bcast")
 
     def propagate_mean(self, X0: torch.Tensor, n_layers: int, out: Optional[torch.Tensor] = None,
@@ -143,8 +170,9 @@ class NormGraph:
         partial, counters = self._scr(dim)
         check(lib().lgc_propagate_mean(_ptr(self.rowptr), _ptr(self.colidx), _ptr(self.val), _ptr(self.chunk_row),
                                        _ptr(self.chunk_start), _ptr(self.row_chunk_base), self.n_chunks, n, dim,
-                                       int(n_layers), _ptr(X0), _ptr(out), _ptr(tmp[0]), _ptr(tmp[1]), _ptr(partial),
-                                       _ptr(counters), _stream()), "propagate_mean")
+                                       int(n_layers), _ptr(self.row_order()), self.long_row(), _ptr(X0), _ptr(out),
+                                       _ptr(tmp[0]), _ptr(tmp[1]), _ptr(partial), _ptr(counters), _stream()),
+              "propagate_mean")
         return out
 
     # algorithmic bytes of one layer, SURVEY.md §8(d): no-reuse model

@@ -56,7 +56,18 @@ def test_propagation_properties_fullsize(dev, shape):
     cuts = [0, n // 5, n // 2, n]
     for r0, r1 in zip(cuts[:-1], cuts[1:]):
         g.spmm(a, out=out, row_begin=r0, row_end=r1)
-    assert torch.equal(out, l1)
+    # a row's summation order depends on the path the launch picks for it (warp-per-row threshold sized to the
+    # launch), so range launches equal the full launch to fp32 round-off, and bit for bit at a pinned threshold
+    assert (out - l1).abs().max() <= 2e-6 * l1.abs().max()
+    from lgcnhs_b200._lib import lib
+    lib().lgc_spmm_long_row(256)
+    try:
+        full = g.spmm(a)
+        for r0, r1 in zip(cuts[:-1], cuts[1:]):
+            g.spmm(a, out=out, row_begin=r0, row_end=r1)
+        assert torch.equal(out, full)
+    finally:
+        lib().lgc_spmm_long_row(0)
     # (6) spectral bound: |A_hat x|_2 <= |x|_2 (eigenvalues of D^-1/2 A D^-1/2 lie in [-1, 1])
     assert l1.double().norm() <= a.double().norm() * (1 + 1e-6)
 
