@@ -8,12 +8,12 @@ import numpy as np, torch  # noqa: E402
 from lgcnhs_b200 import ops  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--what", default="prop", choices=["prop", "spread", "both"])
+ap.add_argument("--what", default="prop", choices=["prop", "spread", "both", "eval", "all"])
 ap.add_argument("--shape", default="ml-20m")
 ap.add_argument("--steps", type=int, default=2)
 a = ap.parse_args()
 dev = torch.device("cuda:0")
-if a.what in ("prop", "both"):
+if a.what in ("prop", "both", "all"):
     d = bench.load_shape(a.shape)
     adj_np, _ = bench.train_adj(d)
     n = d.n_users + d.n_items
@@ -24,7 +24,7 @@ if a.what in ("prop", "both"):
         E = g.propagate_mean(x0, 3)
     torch.cuda.synchronize()
     print("prop ok", float(E.abs().sum()))
-if a.what in ("spread", "both"):
+if a.what in ("spread", "both", "all"):
     d = bench.load_shape("ml-1m")
     tr, va, _ = d.split()
     sel = np.concatenate([tr, va])
@@ -33,3 +33,15 @@ if a.what in ("spread", "both"):
         idx, val = eng.recommend(float(lam), 20)
     torch.cuda.synchronize()
     print("spread ok", int(idx.sum()))
+if a.what in ("eval", "all"):
+    # fused full-rank top-20 (lgc_score_topk) on the amazon-book shape
+    d = bench.load_shape("amazon-book")
+    tr, va, _ = d.split()
+    torch.manual_seed(42)
+    xu = (torch.randn(d.n_users, 64) * 0.1).to(dev)
+    xi = (torch.randn(d.n_items, 64) * 0.1).to(dev)
+    seen = ops.seen_csr(torch.from_numpy(d.users[tr]).to(dev), torch.from_numpy(d.items[tr]).to(dev), d.n_users, d.n_items)
+    for _ in range(2):
+        idx, _ = ops.score_topk(xu, xi, 20, seen, want_values=False)
+    torch.cuda.synchronize()
+    print("eval ok", int(idx.sum()))
