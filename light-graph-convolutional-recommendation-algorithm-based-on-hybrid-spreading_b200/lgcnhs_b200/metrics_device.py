@@ -42,12 +42,30 @@ def accuracy_device(user_pos_items_dict: dict, recommendations: torch.Tensor, k:
     return m["precision"], m["recall"], m["f1"], m["ndcg"]
 
 
+_COOC_CACHE: dict = {}
+
+
+def _cooc_engine(interaction_mat: np.ndarray, dev: torch.device) -> ops.SpreadingEngine:
+    """Engine (packed operands + co-occurrence matrix) of a dense 0/1 interaction matrix, cached on the array's
+    identity: train.py evaluates with the SAME matrix every epoch_per_eval steps (train.py:156-160)."""
+    key = (interaction_mat.__array_interface__["data"][0], interaction_mat.shape)
+    hit = _COOC_CACHE.get(key)
+    if hit is not None and hit[1] is interaction_mat:
+        return hit[0]
+    U, M = int(interaction_mat.shape[0]), int(interaction_mat.shape[1])
+    u, i = np.nonzero(interaction_mat)
+    eng = ops.SpreadingEngine(U, M, torch.from_numpy(u).to(dev), torch.from_numpy(i).to(dev))
+    eng.cooccurrence()
+    _COOC_CACHE.clear()
+    _COOC_CACHE[key] = (eng, interaction_mat)
+    return eng
+
+
 def diversity_device(recommendations: torch.Tensor, item_degree_dict: dict, interaction_mat: np.ndarray, k: int) -> tuple:
     dev = _dev()
     rec = recommendations.detach().to(dev).long().contiguous()
     U, M = int(interaction_mat.shape[0]), int(interaction_mat.shape[1])
-    u, i = np.nonzero(interaction_mat)
-    eng = ops.SpreadingEngine(U, M, torch.from_numpy(u).to(dev), torch.from_numpy(i).to(dev))
+    eng = _cooc_engine(interaction_mat, dev)
     deg = np.zeros(M, dtype=np.int32)
     for it, c in item_degree_dict.items():
         if 0 <= int(it) < M:

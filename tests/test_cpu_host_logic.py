@@ -142,3 +142,23 @@ def test_reference_main_imports_resolve_to_dropin(tmp_path):
     for l in lines:
         if not l.startswith("const"):
             assert "/root/reference" not in l, f"module resolved to the reference instead of the drop-in: {l}"
+
+
+def test_partition_cost_weighting_and_metric_sums():
+    """Host logic added for the multi-GPU partition (chunk-path rows cost more) and the device metrics reduction."""
+    from lgcnhs_b200.dist import partition_rows_by_nnz
+    from lgcnhs_b200.ops import metrics_from_sums
+
+    deg = np.r_[np.full(1000, 50), np.full(10, 5000)]            # 1000 short rows, then 10 long (chunk-path) rows
+    rowptr = np.r_[0, np.cumsum(deg)]
+    plain = partition_rows_by_nnz(rowptr, 2, chunk_weight=1.0, long_row=256)
+    heavy = partition_rows_by_nnz(rowptr, 2, chunk_weight=2.0, long_row=256)
+    assert plain[0] == heavy[0] == 0 and plain[-1] == heavy[-1] == 1010
+    assert heavy[1] > plain[1]                                    # the part holding the long rows gets fewer of them
+    cost = lambda a, b, w: sum(d * (w if d > 256 else 1.0) + 1 for d in deg[a:b])  # noqa: E731
+    assert abs(cost(0, heavy[1], 2.0) - cost(heavy[1], 1010, 2.0)) <= 2 * 5000 * 2.0 + 2
+    # sums -> the reference's rounded metrics (metrics/accurate.py, metrics/diversity.py closed forms)
+    m = metrics_from_sums([30.0, 2.5, 4.0, 10.0, 180.0, 54.0], n_users=10, k=3)
+    assert m["precision"] == 1.0 and m["recall"] == 0.25 and m["ndcg"] == 0.4
+    assert m["f1"] == round(2 * 1.0 * 0.25 / 1.25, 5)
+    assert m["H"] == round(1 - 180.0 / (10 * 9 * 3), 5) and m["I"] == round(54.0 / (10 * 3 * 2), 5)
