@@ -209,6 +209,9 @@ int lgc_score_topk(const float* Xu, const float* Xi, int64_t u0, int64_t u1, int
 int lgc_peer_barrier(const int32_t* local_flags, int32_t* const* peer_flags_host, int32_t my_rank,
                      int32_t n_peers, int32_t epoch, lgc_stream_t stream);
 
+/* Tuning knob of lgc_score_topk: CTA size (256 or 512 threads) of the 128-user tile variant. */
+int lgc_score_topk_config(int32_t threads);
+
 /* ------------------------------------------------------------------------------------
  * (N3) Structured negative sampling for BPR.  Replaces
  * torch_geometric.utils.structured_negative_sampling as used by sampleMiniBatch

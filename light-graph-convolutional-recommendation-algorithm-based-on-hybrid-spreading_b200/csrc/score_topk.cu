@@ -231,7 +231,10 @@ topk_rows_kernel(const float* __restrict__ S, int n_rows, int n, int64_t lds, co
 // score[users, items] = -1024 followed by torch.topk) or are dropped (the filtered lists of the
 // spreading family); an optional multiplier matrix fuses the Hadamard product F_new = G * F of
 // /root/reference/model/SpreadLightGCN/model.py:151 into the same pass.
-constexpr int kFTI = 128, kFThreads = 256;
+constexpr int kFTI = 128;
+static int g_score_topk_threads = 512;  // CTA size of the 128-user tile variant: 512 threads (4 x 8 register tile, 16
+                                        // warps hide the LDS latency) measured 19.1 ms vs 21.4 ms for 256 threads (8 x 8)
+                                        // on the amazon-book shape (lgc_score_topk_config)
 
 // d = a * b + c on two packed fp32 lanes (Blackwell FFMA2): each half is an IEEE round-to-nearest fmaf, so the
 // result is bit-identical to the scalar loop of lgc_score_block at half the FMA-pipe issue slots (a scalar
@@ -267,16 +270,17 @@ __device__ __forceinline__ bool csr_contains(const int32_t* __restrict__ ptr, co
 // TU users per CTA (64 or 128): a thread owns TU/16 users x 8 items.  The loop is bound by the bytes shared
 // memory returns to registers per FMA, so the larger tile (8 x 8: 64 B per 64 FMAs) is used whenever the
 // candidate buffers of 128 rows fit next to the double-buffered item tile (k <= 32).
-template <int DIM, int TU, int CAP, bool MUL>
-__global__ void __launch_bounds__(kFThreads, ((TU == 64 && CAP <= 64) ? 2 : 1))
+template <int DIM, int TU, int CAP, bool MUL, int NT>
+__global__ void __launch_bounds__(NT, ((TU == 64 && CAP <= 64 && NT == 256) ? 2 : 1))
 score_topk_kernel(const float* __restrict__ Xu, const float* __restrict__ Xi, int64_t u0, int64_t u1, int n_items,
                   const int32_t* __restrict__ seen_ptr, const int32_t* __restrict__ seen_idx, float fill,
                   int exclude_seen, const float* __restrict__ mul, int64_t ldmul, int k,
                   int64_t* __restrict__ out_idx, float* __restrict__ out_val) {
   constexpr int E = CAP / 32;
-  constexpr int UT = TU / 16;                       // users per thread
+  constexpr int UT = TU / (NT / 16);                // users per thread
   constexpr int CH = DIM / 4;                       // float4 chunks per embedding row
-  constexpr int LDI = (kFTI * CH) / kFThreads;      // item-tile float4 loads per thread
+  constexpr int LDI = (kFTI * CH) / NT;             // item-tile float4 loads per thread
+  constexpr int NW = NT / 32;                       // warps
   constexpr int NS = UT * 8;                        // scores per thread and tile
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float (*sU)[TU + 4] = reinterpret_cast<float (*)[TU + 4]>(smem_raw);
@@ -293,7 +297,7 @@ score_topk_kernel(const float* __restrict__ Xu, const float* __restrict__ Xi, in
   const int64_t ub = u0 + (int64_t)blockIdx.x * TU;
 
   if (tid < TU) { thr[tid] = 0ull; cnt[tid] = 0; res[tid] = 0; }
-  for (int f = tid; f < TU * CH; f += kFThreads) {
+  for (int f = tid; f < TU * CH; f += NT) {
     const int r = f % TU, c = f / TU;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ub + r < u1) a = __ldg(reinterpret_cast<const float4*>(Xu + (ub + r) * DIM + c * 4));
@@ -304,7 +308,7 @@ score_topk_kernel(const float* __restrict__ Xu, const float* __restrict__ Xi, in
   auto fetch = [&](int ib) {
 #pragma unroll
     for (int m = 0; m < LDI; ++m) {
-      const int f = tid + kFThreads * m, r = f % kFTI, c = f / kFTI;
+      const int f = tid + NT * m, r = f % kFTI, c = f / kFTI;
       pre[m] = ib + r < n_items ? __ldg(reinterpret_cast<const float4*>(Xi + (int64_t)(ib + r) * DIM + c * 4))
                                 : make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -313,7 +317,7 @@ score_topk_kernel(const float* __restrict__ Xu, const float* __restrict__ Xi, in
     float (*sI)[kFTI + 4] = sI0 + buf * DIM;
 #pragma unroll
     for (int m = 0; m < LDI; ++m) {
-      const int f = tid + kFThreads * m, r = f % kFTI, c = f / kFTI;
+      const int f = tid + NT * m, r = f % kFTI, c = f / kFTI;
       sI[c * 4 + 0][r] = pre[m].x; sI[c * 4 + 1][r] = pre[m].y; sI[c * 4 + 2][r] = pre[m].z; sI[c * 4 + 3][r] = pre[m].w;
     }
   };
@@ -427,16 +431,16 @@ score_topk_kernel(const float* __restrict__ Xu, const float* __restrict__ Xi, in
       np = keep;
       // the one barrier of the tile: every thread is past the FMA loop and has staged its part of the next tile
       if (!__syncthreads_or(np > 0)) break;
-      for (int rr = 0; rr < TU / 8; ++rr) {  // each warp compacts the full buffers among its TU/8 rows
-        const int row = warp * (TU / 8) + rr;
+      for (int rr = 0; rr < TU / NW; ++rr) {  // each warp compacts the full buffers among its TU/8 rows
+        const int row = warp * (TU / NW) + rr;
         if (cnt[row] >= CAP) compact_row(row, CAP);
       }
       __syncthreads();
     }
   }
 
-  for (int rr = 0; rr < TU / 8; ++rr) {
-    const int row = warp * (TU / 8) + rr;
+  for (int rr = 0; rr < TU / NW; ++rr) {
+    const int row = warp * (TU / NW) + rr;
     const int64_t u = ub + row;
     if (u >= u1) continue;
     int c = cnt[row];
@@ -517,6 +521,12 @@ extern "C" int lgc_topk_rows(const float* S, int64_t n_rows, int64_t n_cols, int
   return LGC_OK;
 }
 
+extern "C" int lgc_score_topk_config(int32_t threads) {
+  LGC_REQUIRE(threads == 256 || threads == 512, "score_topk config: threads must be 256 or 512");
+  g_score_topk_threads = threads;
+  return LGC_OK;
+}
+
 extern "C" int lgc_score_topk(const float* Xu, const float* Xi, int64_t u0, int64_t u1, int64_t n_items, int32_t dim,
                               const int32_t* seen_ptr, const int32_t* seen_idx, float fill, int32_t exclude_seen,
                               const float* mul, int64_t ldmul, int32_t k, int64_t* out_idx, float* out_val,
@@ -528,17 +538,22 @@ extern "C" int lgc_score_topk(const float* Xu, const float* Xi, int64_t u0, int6
   LGC_REQUIRE(((uintptr_t)Xu & 15) == 0 && ((uintptr_t)Xi & 15) == 0, "score_topk: embeddings must be 16-byte aligned");
   LGC_REQUIRE((seen_ptr == nullptr) == (seen_idx == nullptr), "score_topk: seen_ptr / seen_idx mismatch");
   LGC_REQUIRE(!mul || ldmul >= n_items, "score_topk: multiplier leading dimension smaller than the row");
-#define LGC_ST_LAUNCH(D, TUV, CAPV, MULV)                                                                       \
+#define LGC_ST_LAUNCH_NT(D, TUV, CAPV, MULV, NTV)                                                               \
   do {                                                                                                          \
     static bool attr = false;                                                                                   \
     constexpr size_t smem = score_topk_smem<D, TUV, CAPV>();                                                    \
     if (!attr) {                                                                                                \
-      LGC_CUDA(cudaFuncSetAttribute(score_topk_kernel<D, TUV, CAPV, MULV>,                                      \
+      LGC_CUDA(cudaFuncSetAttribute(score_topk_kernel<D, TUV, CAPV, MULV, NTV>,                                 \
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                   \
       attr = true;                                                                                              \
     }                                                                                                           \
-    score_topk_kernel<D, TUV, CAPV, MULV><<<(unsigned)ceil_div(u1 - u0, TUV), kFThreads, smem, stream>>>(       \
+    score_topk_kernel<D, TUV, CAPV, MULV, NTV><<<(unsigned)ceil_div(u1 - u0, TUV), NTV, smem, stream>>>(        \
         Xu, Xi, u0, u1, (int)n_items, seen_ptr, seen_idx, fill, exclude_seen, mul, ldmul, k, out_idx, out_val); \
+  } while (0)
+#define LGC_ST_LAUNCH(D, TUV, CAPV, MULV)                                                                       \
+  do {                                                                                                          \
+    if (TUV == 128 && g_score_topk_threads == 512) LGC_ST_LAUNCH_NT(D, 128, CAPV, MULV, 512);                   \
+    else LGC_ST_LAUNCH_NT(D, TUV, CAPV, MULV, 256);                                                             \
   } while (0)
   // 128-user tiles (8 x 8 register tile) while the candidate buffers fit; small problems keep 64-user tiles so
   // that the grid still covers the SMs
@@ -559,6 +574,7 @@ extern "C" int lgc_score_topk(const float* Xu, const float* Xi, int64_t u0, int6
   }
 #undef LGC_ST_DIM
 #undef LGC_ST_LAUNCH
+#undef LGC_ST_LAUNCH_NT
   LGC_LAUNCH_CHECK("score_topk_kernel");
   return LGC_OK;
 }

@@ -46,6 +46,7 @@ _SIGS = {
     "lgc_negative_sample": (C.c_int, [_p, _p, _i64, _p, _i64, _p, _p, _i64, _i64, _i32, C.c_uint64, _p, _p, _p, _p, _p]),
     "lgc_metrics_scratch_bytes": (_i64, [_i64]),
     "lgc_metrics_topk": (C.c_int, [_p, _i64, _i32, _i64, _p, _p, _p, _i64, _p, _p, _p, _p]),
+    "lgc_score_topk_config": (C.c_int, [_i32]),
     "lgc_mask_from_csr": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _p]),
     "hs_degrees": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p]),
     "hs_pack_a": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _i64, _p]),

@@ -204,15 +204,23 @@ def test_score_topk_fused_hadamard_and_exclusion(dev):
     assert not any((u, int(i)) in seen_set for u in range(U) for i in idx[u].cpu())
 
 
+@pytest.mark.parametrize("threads", [256, 512])
 @pytest.mark.parametrize("k", [20, 50, 100])
-def test_score_topk_large_user_tiles(dev, k):
-    """>= 128 * n_sms users selects the 128-user CTA tile (8 x 8 register tile); k = 100 falls back to 64-user tiles."""
+def test_score_topk_large_user_tiles(dev, k, threads):
+    """>= 128 * n_sms users selects the 128-user CTA tile (256 threads: 8 x 8 register tile, 512 threads: 4 x 8);
+    k > 32 falls back to 64-user tiles."""
     from lgcnhs_b200 import ops
+    from lgcnhs_b200._lib import lib
 
     U, M = 19100, 389
     uw, iw, su, si = _rand_problem(U, M, 64, 77, 40000)
     seen = ops.seen_csr(su.to(dev), si.to(dev), U, M)
     dense = ops.score_block(uw.to(dev), iw.to(dev), 0, U, seen)
     ridx, rval = ops.topk_rows(dense, k)
-    idx, val = ops.score_topk(uw.to(dev), iw.to(dev), k, seen)
+    default = 512
+    lib().lgc_score_topk_config(threads)
+    try:
+        idx, val = ops.score_topk(uw.to(dev), iw.to(dev), k, seen)
+    finally:
+        lib().lgc_score_topk_config(default)
     assert torch.equal(val, rval) and torch.equal(idx, ridx)

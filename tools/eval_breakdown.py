@@ -28,10 +28,14 @@ def timeit(fn, n=5):
     return e0.elapsed_time(e1) / n
 
 
+from lgcnhs_b200._lib import lib  # noqa: E402
+
 print(f"shape {shape}: U={U} M={M}  score flops = {2.0 * U * M * 64 / 1e9:.1f} GFLOP")
-for k in (20, 100):
-    ms = timeit(lambda: ops.score_topk(xu, xi, k, seen, want_values=False))
-    print(f"fused score_topk k={k:3d}: {ms:8.3f} ms  {U / ms * 1e3:12.0f} users/s  {2.0 * U * M * 64 / ms / 1e9:8.1f} TFLOP/s fp32")
+for threads in (256, 512):
+    lib().lgc_score_topk_config(threads)
+    for k in (20, 100):
+        ms = timeit(lambda: ops.score_topk(xu, xi, k, seen, want_values=False))
+        print(f"fused score_topk ({threads} thr) k={k:3d}: {ms:8.3f} ms  {U / ms * 1e3:12.0f} users/s  {2.0 * U * M * 64 / ms / 1e9:8.1f} TFLOP/s fp32")
 blk = 8192
 buf = torch.empty((blk, (M + 3) // 4 * 4), dtype=torch.float32, device=dev)
 
