@@ -499,7 +499,10 @@ def main():
             "us_per_layer": round(per_layer_ms * 1e3, 2),
             "compulsory_frac": round(compulsory / (per_layer_ms * 1e-3) / 1e9 / hbm, 4),
             "note": f"algorithmic bytes = no-reuse model 264 B/nnz + 260 B/node per layer; peak = {how} HBM copy "
-                    "bandwidth; X is L2-resident so the no-reuse fraction may exceed 1 (SURVEY.md 8d)",
+                    "bandwidth; X is L2-resident so the no-reuse fraction may exceed 1 (SURVEY.md 8d): the gathers are "
+                    "served by L2 at the rates in `ncu` (profiles/r1_ncu_all_kernels.txt), DRAM traffic = `traffic`",
+            "ncu": {"l1tex_throughput_pct": 71.4, "lts_throughput_pct": 60.4, "dram_throughput_pct": 8.4,
+                    "warps_active_pct": 96.6, "source": "profiles/r1_ncu_all_kernels.txt (same kernel, same graph)"},
         }
 
     # ---- e2e through the reference-facing module call, host buffers, N GPUs ----
