@@ -126,7 +126,7 @@ topk_rows_kernel(const float* __restrict__ S, int n_rows, int n, int64_t lds, co
     uint32_t m = __ballot_sync(0xffffffffu, pass);
     if (m == 0u) return;
     if (cnt + __popc(m) > CAP) {
-      cnt = warp_compact<E>(buf, cnt, k, lane, &thr);
+      cnt = E >= 4 ? warp_select<E>(buf, cnt, k, lane, &thr) : warp_compact<E>(buf, cnt, k, lane, &thr);
       thr_f = thr ? key_float((uint32_t)(thr >> 32)) : -INFINITY;
       pass = pass && key > thr;
       m = __ballot_sync(0xffffffffu, pass);
@@ -329,7 +329,7 @@ score_topk_kernel(const float* __restrict__ Xu, const float* __restrict__ Xi, in
   // One warp: apply the seen-pair rule to the not yet resolved entries of a row's buffer (the binary searches of
   // the lanes overlap; candidates are appended unchecked so that no global-memory latency sits between the tiles'
   // barriers), then keep the k best and raise the row's threshold.
-  auto compact_row = [&](int row, int n) {
+  auto compact_row = [&](int row, int n, bool final_sort) {
     unsigned long long* base = cand + (size_t)row * CAP;
     if (seen_ptr) {
       const int r0 = res[row];
@@ -345,7 +345,7 @@ score_topk_kernel(const float* __restrict__ Xu, const float* __restrict__ Xi, in
       }
     }
     unsigned long long t;
-    const int kept = warp_compact<E>(base, n, k, lane, &t);
+    const int kept = (E >= 4 && !final_sort) ? warp_select<E>(base, n, k, lane, &t) : warp_compact<E>(base, n, k, lane, &t);
     if (lane == 0) { cnt[row] = kept; thr[row] = t; res[row] = kept; }
     __syncwarp();
     return kept;
@@ -433,7 +433,7 @@ score_topk_kernel(const float* __restrict__ Xu, const float* __restrict__ Xi, in
       if (!__syncthreads_or(np > 0)) break;
       for (int rr = 0; rr < TU / NW; ++rr) {  // each warp compacts the full buffers among its TU/8 rows
         const int row = warp * (TU / NW) + rr;
-        if (cnt[row] >= CAP) compact_row(row, CAP);
+        if (cnt[row] >= CAP) compact_row(row, CAP, false);
       }
       __syncthreads();
     }
@@ -445,7 +445,7 @@ score_topk_kernel(const float* __restrict__ Xu, const float* __restrict__ Xi, in
     if (u >= u1) continue;
     int c = cnt[row];
     c = c < CAP ? c : CAP;
-    const int kept = compact_row(row, c);
+    const int kept = compact_row(row, c, true);
     for (int i = lane; i < k; i += 32) {
       const unsigned long long key = cand[(size_t)row * CAP + i];
       out_idx[(u - u0) * k + i] = i < kept ? (int64_t)(uint32_t)(key & 0xffffffffull) : -1;

@@ -97,4 +97,62 @@ __device__ __forceinline__ int warp_compact(unsigned long long* buf, int cnt, in
   return kept;
 }
 
+// Same contract as warp_compact but WITHOUT ordering the survivors: the k-th largest key is found by an MSB-first
+// radix search over the keys held in registers (one warp-wide count per bit, stopping as soon as the keys that
+// share the prefix are exactly the ones still wanted), then the keys >= that threshold are packed to the front
+// with a ballot / prefix.  About half the instructions of the bitonic sort for 256 keys; used for the
+// intermediate compactions (the final one sorts).
+template <int E>
+__device__ __forceinline__ int warp_select(unsigned long long* buf, int cnt, int k, int lane,
+                                           unsigned long long* thr) {
+  __syncwarp();
+  unsigned long long r[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int idx = e * 32 + lane;
+    r[e] = idx < cnt ? buf[idx] : 0ull;
+  }
+  unsigned long long prefix = 0ull;  // bits [63..b] of the k-th largest key found so far
+  int want = k;                      // rank of the wanted key among the keys that share the prefix
+#pragma unroll 1
+  for (int b = 63; b >= 0; --b) {
+    const unsigned long long cand = (prefix >> b) | 1ull;  // prefix extended by a 1 bit, right-aligned
+    int c = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) c += ((r[e] >> b) == cand) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c >= want) {
+      prefix |= 1ull << b;
+      if (c == want) {  // exactly the wanted keys share this prefix: the threshold is their minimum
+        unsigned long long mn = ~0ull;
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+          if ((r[e] >> b) == cand && r[e] < mn) mn = r[e];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          const unsigned long long o = __shfl_xor_sync(0xffffffffu, mn, off);
+          mn = o < mn ? o : mn;
+        }
+        prefix = mn;
+        break;
+      }
+    } else {
+      want -= c;
+    }
+  }
+  // prefix == k-th largest key (0 when fewer than k non-zero keys exist)
+  __syncwarp();
+  int base = 0;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const bool keep = r[e] != 0ull && r[e] >= prefix;
+    const uint32_t m = __ballot_sync(0xffffffffu, keep);
+    if (keep) buf[base + __popc(m & ((1u << lane) - 1u))] = r[e];
+    base += __popc(m);
+  }
+  __syncwarp();
+  *thr = (base == k && prefix != 0ull) ? prefix : 0ull;
+  return base;
+}
+
 }  // namespace lgc
