@@ -126,7 +126,7 @@ topk_rows_kernel(const float* __restrict__ S, int n_rows, int n, int64_t lds, co
     uint32_t m = __ballot_sync(0xffffffffu, pass);
     if (m == 0u) return;
     if (cnt + __popc(m) > CAP) {
-      cnt = E >= 4 ? warp_select<E>(buf, cnt, k, lane, &thr) : warp_compact<E>(buf, cnt, k, lane, &thr);
+      cnt = E >= 2 ? warp_select<E>(buf, cnt, k, lane, &thr) : warp_compact<E>(buf, cnt, k, lane, &thr);
       thr_f = thr ? key_float((uint32_t)(thr >> 32)) : -INFINITY;
       pass = pass && key > thr;
       m = __ballot_sync(0xffffffffu, pass);
