@@ -58,3 +58,28 @@ def test_product_path_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f"{f} reaches into oracle/"
+
+
+def test_ctypes_signatures_match_header_arity():
+    """Every binding in _lib._SIGS takes exactly as many arguments as its declaration in include/lgcnhs.h (a
+    mismatch would corrupt the call frame silently: ctypes cannot check it)."""
+    import re
+
+    from lgcnhs_b200 import _lib
+
+    txt = open(_lib.HEADER_PATH).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    for name, (_, args) in _lib._SIGS.items():
+        m = re.search(r"\b" + name + r"\s*\(([^;]*?)\)\s*;", txt, flags=re.S)
+        assert m, f"{name}: declaration not found"
+        params = m.group(1).strip()
+        n = 0 if params in ("", "void") else len([p for p in params.split(",") if p.strip()])
+        assert n == len(args), f"{name}: header declares {n} parameters, ctypes binding has {len(args)}"
+    # new argument checks that need no device
+    lib = _lib.lib()
+    assert lib.lgc_score_topk(0, 0, 0, 1, 1, 64, 0, 0, 0.0, 0, 0, 0, 1, 0, 0, 0) == -1       # null embeddings
+    assert lib.lgc_metrics_topk(0, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0) == -1                      # null lists
+    assert lib.lgc_peer_barrier(0, None, 0, 1, 1, 0) == -1
+    assert lib.lgc_spmm_long_row(100) == -1 and lib.lgc_spmm_long_row(0) == 0
+    assert lib.lgc_score_topk_config(300) == -1 and lib.lgc_score_topk_config(512) == 0
+    assert lib.lgc_metrics_scratch_bytes(1000) >= 4000
