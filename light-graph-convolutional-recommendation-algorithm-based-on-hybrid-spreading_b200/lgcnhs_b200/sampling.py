@@ -20,17 +20,19 @@ from .ops import seen_csr
 _POS_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
 
 
-def _pos_csr(edge_index: torch.Tensor, num_nodes: int):
-    """Sorted positive-item CSR of the (2, E) user->item edge list, cached on tensor identity."""
+def _pos_csr(edge_index: torch.Tensor, num_nodes):
+    """(num_nodes, sorted positive-item CSR) of the (2, E) user->item edge list, cached on tensor identity — the
+    `edge_index.max()` behind PyG's maybe_num_nodes would otherwise cost a device->host sync on every step."""
     key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, num_nodes)
     hit = _POS_CACHE.get(key)
     if hit is not None and hit[1] is edge_index:
         return hit[0]
-    csr = seen_csr(edge_index[0], edge_index[1], num_nodes, num_nodes)
-    _POS_CACHE[key] = (csr, edge_index)
+    n = int(edge_index.max()) + 1 if num_nodes is None else int(num_nodes)   # max over BOTH rows (quirk P5)
+    csr = seen_csr(edge_index[0], edge_index[1], n, n)
+    _POS_CACHE[key] = ((n, csr), edge_index)
     while len(_POS_CACHE) > 4:
         _POS_CACHE.popitem(last=False)
-    return csr
+    return n, csr
 
 
 def structured_negative_sampling(edge_index: torch.Tensor, num_nodes: Optional[int] = None,
@@ -40,10 +42,8 @@ def structured_negative_sampling(edge_index: torch.Tensor, num_nodes: Optional[i
     if not edge_index.is_cuda:
         raise RuntimeError("structured_negative_sampling: edge_index must be a CUDA tensor (no CPU fallback)")
     edge_index = edge_index if edge_index.dtype == torch.int64 else edge_index.long()
-    if num_nodes is None:
-        num_nodes = int(edge_index.max()) + 1          # PyG maybe_num_nodes: max over BOTH rows (quirk P5)
     dev = edge_index.device
-    ptr, idx = _pos_csr(edge_index, num_nodes)
+    num_nodes, (ptr, idx) = _pos_csr(edge_index, num_nodes)
     eu, ep = edge_index[0].contiguous(), edge_index[1].contiguous()
     n_edges = int(eu.numel())
     if rows is not None:

@@ -1,8 +1,6 @@
 """Drop-in for /root/reference/model/LightGCN/loss.py: BPRLoss and sampleMiniBatch with the
 reference's signatures.  BPRLoss runs as ONE fused CUDA kernel forward and one backward
 (lgc_bpr_rows) instead of ~12 elementwise/reduce launches."""
-import random
-
 import torch
 
 from lgcnhs_b200 import ops
@@ -37,9 +35,10 @@ def BPRLoss(users_emb_final: torch.Tensor, users_emb_0: torch.Tensor,
 
 def sampleMiniBatch(batch_size: int, edge_index: torch.Tensor) -> tuple:
     """batch_size (user, pos, neg) triplets (reference loss.py:46-70).  The reference negative-samples
-    ALL edges and then keeps batch_size of them with `random.choices` (Python RNG, with
-    replacement); picking the rows first and sampling negatives only for those is the same
-    distribution at 1/E-th of the work."""
+    ALL edges and then keeps batch_size of them with `random.choices` (uniform, with replacement, Python RNG,
+    unseeded); picking the rows first and sampling negatives only for those is the same distribution at 1/E-th
+    of the work.  The row indices are drawn on the device (torch.randint: uniform with replacement, like
+    random.choices) so that the step never synchronises with the host."""
     n_edges = edge_index.shape[1]
-    indices = torch.tensor(random.choices(range(n_edges), k=batch_size), device=edge_index.device)
+    indices = torch.randint(n_edges, (batch_size,), device=edge_index.device)
     return structured_negative_sampling(edge_index, rows=indices)
