@@ -10,7 +10,6 @@ import numpy as np
 import torch
 
 from lgcnhs_b200 import ops
-from lgcnhs_b200._lib import check, lib
 from utils.log import logger
 from utils.wrapper import calTimes
 

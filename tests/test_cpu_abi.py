@@ -1,6 +1,4 @@
 """CPU: the C-ABI library builds/loads without a GPU and exports every symbol include/lgcnhs.h declares."""
-import ctypes
-
 import pytest
 
 

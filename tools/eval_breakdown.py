@@ -4,7 +4,7 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
-import numpy as np, torch  # noqa: E402
+import torch  # noqa: E402
 from lgcnhs_b200 import ops  # noqa: E402
 
 dev = torch.device("cuda:0")

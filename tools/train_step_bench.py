@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import bench  # noqa: E402
 import _stub_const  # noqa: E402
-import numpy as np, torch  # noqa: E402
+import torch  # noqa: E402
 
 _stub_const.install()
 from lgcnhs_b200.trainer import FusedBPRTrainer  # noqa: E402
