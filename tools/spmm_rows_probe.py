@@ -33,9 +33,11 @@ def timeit(a, b, reps=10):
 
 from lgcnhs_b200._lib import lib  # noqa: E402
 
-for T in [int(t) for t in os.environ.get("PROBE_LONG_ROW", "0").split(",")]:
+for UNR in [int(t) for t in os.environ.get("PROBE_UNROLL", "0").split(",")]:
+  lib().lgc_spmm_config(UNR)
+  for T in [int(t) for t in os.environ.get("PROBE_LONG_ROW", "0").split(",")]:
     lib().lgc_spmm_long_row(T)
-    print("long_row =", T)
+    print("unroll =", UNR, "long_row =", T)
     for name, a, b in (("all rows", 0, n), ("user rows", 0, d.n_users), ("item rows", d.n_users, n),
                        ("1/8 of user rows", 0, d.n_users // 8), ("1/8 of item rows", d.n_users, d.n_users + d.n_items // 8)):
         nnz = int(rp[b] - rp[a])
