@@ -489,10 +489,13 @@ class SpreadingEngine:
         return self.C
 
     def sweep(self, lambdas, k: int, test_pos: Optional[tuple] = None, filtered: bool = True,
-              gscore: Optional[torch.Tensor] = None, diversity: bool = True):
-        """The findLambda.py:83-116 loop on the device: G once, then per lambda  HybridS -> A.W [-> * gscore] ->
-        filtered top-k -> six metric sums, with no host round trip inside the loop.  Returns (sums float64
-        (n_lambda, 6) on the HOST after ONE device->host copy, list of per-lambda metric dicts)."""
+              gscore: Optional[torch.Tensor] = None, diversity: bool = True, layer0: Optional[tuple] = None):
+        """The findLambda.py:83-116 loop on the device: G once, then per lambda  HybridS -> A.W [-> * G_score] ->
+        filtered top-k -> six metric sums, with no host round trip inside the loop.  The fusion factor G_score
+        (getAllocateMat) is either a dense (U, M) matrix `gscore` or, better, `layer0 = (Xu, Xi, seen_csr)`: the
+        layer-0 score tiles are then recomputed and multiplied with F inside lgc_score_topk and G_score is never
+        materialised.  Returns (sums float64 (n_lambda, 6) on the HOST after ONE device->host copy, list of
+        per-lambda metric dicts)."""
         if self.G is None:
             self.general_w()
         cooc = self.cooccurrence() if diversity else None
@@ -501,7 +504,13 @@ class SpreadingEngine:
         sums = torch.zeros((len(lambdas), 6), dtype=torch.float64, device=self.dev)
         F = torch.empty((self.U, _pad(self.M, 4)), dtype=torch.float32, device=self.dev)[:, : self.M]
         for n, lam in enumerate(lambdas):
-            idx, _ = self.recommend(lam, k, filtered=filtered, gscore=gscore, F_out=F)
+            if layer0 is not None:
+                xu, xi, seen = layer0
+                self.scale(lam)
+                self.resource(out=F)
+                idx, _ = score_topk(xu, xi, k, seen, fill=-1024.0, exclude_seen=filtered, mul=F, want_values=False)
+            else:
+                idx, _ = self.recommend(lam, k, filtered=filtered, gscore=gscore, F_out=F)
             topk_metrics(idx, self.M, test_pos, cooc, deg, out=sums[n])
         host = sums.cpu()
         return host, [metrics_from_sums(host[n].tolist(), self.U, k) for n in range(len(lambdas))]

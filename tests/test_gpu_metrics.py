@@ -43,11 +43,11 @@ def test_metrics_match_reference_golden(dev):
 
 def test_metrics_duplicates_and_padding(dev):
     """Lists with a repeated item and -1 padding: the reference intersects SETS for H and skips equal ids for I."""
-    from lgcnhs_b200 import ops
-    import metrics.diversity as D
     import _stub_const
 
     _stub_const.install()
+    import metrics.diversity as D
+    from lgcnhs_b200 import ops
     U, M, k = 40, 60, 6
     g = np.random.default_rng(5)
     users = g.integers(0, U, 600)
@@ -97,3 +97,48 @@ def test_lambda_sweep_matches_per_lambda_oracle(dev):
         got = [m["precision"], m["recall"], m["f1"], m["ndcg"], m["H"], m["I"]]
         # ids can differ at float ties between the fp64 oracle and the fp32 device scores: 2e-4 covers one swapped hit
         assert np.allclose(got, [p, r, f1, n, H, I], atol=2e-4), (lam, got, [p, r, f1, n, H, I])
+
+
+def test_find_lambda_fusion_sweep_matches_reference_pipeline(dev, tmp_path):
+    """N4: findLambda.py with the fusion recommender — per lambda F_new = G_score * (A . HybridS), filtered top-k,
+    six metrics — against the oracle pipeline; writes the reference's CSV."""
+    import _stub_const
+    import pandas as pd
+
+    _stub_const.install()
+    from lgcnhs_b200.find_lambda import find_lambda
+    from lgcnhs_b200.synth import synth_shape
+    from metrics.accurate import getAccurateMetrics
+    from metrics.diversity import getDiversityMetrics
+    from model.LightGCN.model import LightGCN
+    from oracle import lightgcn_oracle as LO
+
+    d = synth_shape("small")
+    tr, va, te = d.split()
+    U, M, k = d.n_users, d.n_items, 10
+    df = lambda s: pd.DataFrame({"user_id": d.users[s], "item_id": d.items[s]})  # noqa: E731
+    torch.manual_seed(42)
+    model = LightGCN(U, M, 64, 3)
+    lams = [0.0, 0.5, 1.0]
+    frame = find_lambda(U, M, df(tr), df(va), df(te), k, model=model, lambdas=lams, save_dir=str(tmp_path) + "/")
+    assert list(frame.columns) == ["lambda", "precision", "recall", "f1", "ndcg", "H", "I"]
+    assert (tmp_path / f"lambda_evaluation_{k}.csv").exists()
+    tv = np.r_[tr, va]
+    A = S.interaction_matrix(U, M, d.users[tv], d.items[tv])
+    Gm = S.get_spreading_general_mat(A)
+    uw, iw = model.users_emb.weight.detach().cpu(), model.items_emb.weight.detach().cpu()
+    e_tv = torch.from_numpy(np.stack([d.users[tv], d.items[tv]]))
+    Gs = LO.masked_score(uw, iw, e_tv).numpy()
+    test_dict = {}
+    for u, i in zip(d.users[te].tolist(), d.items[te].tolist()):
+        test_dict.setdefault(u, []).append(i)
+    deg = {i: int(c) for i, c in enumerate(A.sum(0)) if c > 0}
+    for n, lam in enumerate(lams):
+        F_new = S.fused_resource(Gs, S.get_resource(A, S.hybrids(A, Gm, lam)))
+        idx, _ = S.recommend_fast(F_new, A, k)
+        rec = torch.from_numpy(idx.astype(np.int64))
+        p, r, f1, nd = getAccurateMetrics(test_dict, rec, k)
+        H, I = getDiversityMetrics(rec, deg, A, k)
+        got = frame.iloc[n][["precision", "recall", "f1", "ndcg", "H", "I"]].to_numpy(dtype=float)
+        # ids can differ at float ties (F_new has many exact zeros and fp32-vs-fp64 near-ties): a few swapped items
+        assert np.allclose(got, [p, r, f1, nd, H, I], atol=5e-4), (lam, got, [p, r, f1, nd, H, I])
