@@ -391,13 +391,13 @@ def training_leg(dev, steps: int, warmup: int):
     from model.LightGCN.loss import sampleMiniBatch
 
     # one reference iteration (train.py:125-144): sample a mini-batch (device negative sampler), forward, BPR,
-    # backward, Adam.  U < M on this shape, so the sampler's [0, max id] range quirk never needs the clamp.
+    # backward, Adam.
     train_ei = torch.from_numpy(np.stack([d.users[tr], d.items[tr]])).to(dev)
     torch.manual_seed(42)
 
     def one_step():
         u, p, n = sampleMiniBatch(B, train_ei)
-        return trainer.step(u, p, n.clamp_(max=d.n_items - 1))
+        return trainer.step(u, p, n)
 
     for i in range(max(warmup, 3)):
         one_step()

@@ -3,6 +3,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -42,6 +43,20 @@ void note_launch(int n = 1);
       LGC_FAIL(LGC_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(_e)); \
     ::lgc::note_launch();                                                           \
   } while (0)
+
+// "once per device" guard for cudaFuncSetAttribute: the dynamic-shared-memory opt-in belongs to a device's
+// context, so a process that drives several GPUs must set it on each of them.  Thread-safe; a duplicated set from
+// two racing threads is harmless.
+struct DeviceOnce {
+  std::atomic<unsigned long long> done{0ull};
+  static int dev() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d & 63;
+  }
+  bool need() const { return !((done.load(std::memory_order_acquire) >> dev()) & 1ull); }
+  void mark() { done.fetch_or(1ull << dev(), std::memory_order_release); }
+};
 
 inline int num_sms() {
   static int n = 0;

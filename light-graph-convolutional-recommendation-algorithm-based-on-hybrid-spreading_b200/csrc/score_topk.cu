@@ -540,12 +540,12 @@ extern "C" int lgc_score_topk(const float* Xu, const float* Xi, int64_t u0, int6
   LGC_REQUIRE(!mul || ldmul >= n_items, "score_topk: multiplier leading dimension smaller than the row");
 #define LGC_ST_LAUNCH_NT(D, TUV, CAPV, MULV, NTV)                                                               \
   do {                                                                                                          \
-    static bool attr = false;                                                                                   \
+    static DeviceOnce attr;                                                                                        \
     constexpr size_t smem = score_topk_smem<D, TUV, CAPV>();                                                    \
-    if (!attr) {                                                                                                \
+    if (attr.need()) {                                                                                                \
       LGC_CUDA(cudaFuncSetAttribute(score_topk_kernel<D, TUV, CAPV, MULV, NTV>,                                 \
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                   \
-      attr = true;                                                                                              \
+      attr.mark();                                                                                               \
     }                                                                                                           \
     score_topk_kernel<D, TUV, CAPV, MULV, NTV><<<(unsigned)ceil_div(u1 - u0, TUV), NTV, smem, stream>>>(        \
         Xu, Xi, u0, u1, (int)n_items, seen_ptr, seen_idx, fill, exclude_seen, mul, ldmul, k, out_idx, out_val); \

@@ -629,11 +629,11 @@ extern "C" int hs_gemm_planes(int32_t kind, const void* A, int64_t lda, const vo
     const int grid = 2 * clusters;
 #define LGC_GEMM_PAIR_CASE(KD, PL)                                                                              \
   if (kind == KD && planes == PL) {                                                                             \
-    static bool attr = false;                                                                                   \
-    if (!attr) {                                                                                                \
+    static DeviceOnce attr;                                                                                        \
+    if (attr.need()) {                                                                                                \
       LGC_CUDA(cudaFuncSetAttribute(umma_gemm_pair_kernel<KD, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                     (int)kSmemBytes));                                                          \
-      attr = true;                                                                                              \
+      attr.mark();                                                                                               \
     }                                                                                                           \
     umma_gemm_pair_kernel<KD, PL><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmBh, p);                   \
   }
@@ -648,11 +648,11 @@ extern "C" int hs_gemm_planes(int32_t kind, const void* A, int64_t lda, const vo
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
 #define LGC_GEMM_CASE(KD, PL)                                                                             \
   if (kind == KD && planes == PL) {                                                                       \
-    static bool attr = false;                                                                             \
-    if (!attr) {                                                                                          \
+    static DeviceOnce attr;                                                                                  \
+    if (attr.need()) {                                                                                          \
       LGC_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<KD, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                     (int)kSmemBytes));                                                    \
-      attr = true;                                                                                        \
+      attr.mark();                                                                                         \
     }                                                                                                     \
     umma_gemm_kernel<KD, PL><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, p);                        \
   }

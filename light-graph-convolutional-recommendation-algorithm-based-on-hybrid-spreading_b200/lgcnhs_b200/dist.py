@@ -100,8 +100,14 @@ class RowPartitionedPropagation:
             self.parts = [[(bu[r], bu[r + 1]), (bi[r], bi[r + 1])] for r in range(self.world)]
         self.my_parts = [(a, b, self.g.chunk_range(a, b)) for a, b in self.parts[self.rank] if b > a]
         self.r0, self.r1 = self.parts[self.rank][0]
-        # replicated activations: two ping-pong layers + the result
-        self.bufs = [torch.zeros((n_nodes, dim), dtype=torch.float32, device=self.dev) for _ in range(3)]
+        # replicated activations: two ping-pong layers + TWO result buffers used alternately by successive calls.
+        # The returned tensor aliases a buffer that peers write with remote stores; with a single result buffer a
+        # faster rank's NEXT call could overwrite it while this rank's consumers still read it.  With two, the
+        # buffer of call n is next written by call n+2, and a peer can only get there after passing a layer
+        # barrier of call n+1, which this rank publishes stream-ordered AFTER its consumers of call n's result
+        # (requirement: consume the result on the stream the propagation was issued on, or clone it).
+        self.bufs = [torch.zeros((n_nodes, dim), dtype=torch.float32, device=self.dev) for _ in range(4)]
+        self._calls = 0
         self._flag = torch.zeros(1, dtype=torch.float32, device=self.dev)
         self.peer_ptrs: list[list[int]] = []
         self.peer_flag_ptrs: list[int] = []
@@ -112,13 +118,13 @@ class RowPartitionedPropagation:
             blobs = [_ipc_export(b) for b in self.bufs] + [_ipc_export(self.flags)]
             gathered: list = [None] * self.world
             dist.all_gather_object(gathered, blobs)
-            for bi in range(3):
+            for bi in range(4):
                 ptrs = []
                 for r in range(self.world):
                     ptrs.append(self.bufs[bi].data_ptr() if r == self.rank else _ipc_import(gathered[r][bi]))
                 self.peer_ptrs.append(ptrs)
             for r in range(self.world):
-                self.peer_flag_ptrs.append(self.flags.data_ptr() if r == self.rank else _ipc_import(gathered[r][3]))
+                self.peer_flag_ptrs.append(self.flags.data_ptr() if r == self.rank else _ipc_import(gathered[r][4]))
         torch.cuda.synchronize()
         dist.barrier()
 
@@ -130,9 +136,11 @@ class RowPartitionedPropagation:
         """x0 is replicated on every rank; returns the replicated E = mean_l A_hat^l x0."""
         g = self.g
         cur = x0
+        res = 2 + (self._calls & 1)
+        self._calls += 1
         for l in range(layers):
             last = l == layers - 1
-            oi = 2 if last else (l & 1)
+            oi = res if last else (l & 1)
             alpha = 1.0 / (layers + 1) if last else 1.0
             if self.mode == "p2p":
                 for a, b, ch in self.my_parts:

@@ -42,6 +42,16 @@ def accuracy_device(user_pos_items_dict: dict, recommendations: torch.Tensor, k:
     return m["precision"], m["recall"], m["f1"], m["ndcg"]
 
 
+def hamming_device(recommendations: torch.Tensor, k: int) -> float:
+    """H alone (item histogram kernel + pair reduction); used where the dense interaction matrix is too large to
+    build on the host and I is skipped."""
+    dev = _dev()
+    rec = recommendations.detach().to(dev).long().contiguous()
+    n_items = int(rec.max()) + 1
+    sums = ops.topk_metrics(rec, n_items).cpu().tolist()
+    return ops.metrics_from_sums(sums, int(rec.shape[0]), k)["H"]
+
+
 _COOC_CACHE: dict = {}
 
 

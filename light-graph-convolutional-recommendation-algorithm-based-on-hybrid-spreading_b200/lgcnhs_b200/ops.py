@@ -83,6 +83,41 @@ class NormGraph:
         self._long_rows: dict[tuple[int, int], int] = {}
         self.use_row_order = os.environ.get("LGCNHS_NO_ROW_ORDER", "0") != "1"
 
+    def transposed(self) -> "NormGraph":
+        """The STRUCTURAL transpose of this operator: entry (r, c, v) -> (c, r, v), values reused, sources ascending
+        per row.  This is the graph the backward pass of propagate needs (dX = A_hat^T dY); re-running gcn_norm on the
+        transposed edge list would normalise by the OUT-degrees instead and is only equal for a symmetric graph."""
+        n, nnz, dev = self.n_nodes, self.nnz, self.device
+        t = object.__new__(NormGraph)
+        t.device, t.n_nodes, t.nnz = dev, n, nnz
+        deg = (self.rowptr[1:] - self.rowptr[:-1]).to(torch.int64)
+        rows = torch.repeat_interleave(torch.arange(n, device=dev, dtype=torch.int64), deg)
+        cols = self.colidx[:nnz].to(torch.int64)
+        order = torch.argsort(cols * n + rows)           # keyed by the old source, old targets ascending inside
+        t.colidx = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+        t.val = torch.empty(max(nnz, 1), dtype=torch.float32, device=dev)
+        t.colidx[:nnz] = rows[order].to(torch.int32)
+        t.val[:nnz] = self.val[:nnz][order]
+        tdeg = torch.bincount(cols, minlength=n)
+        rowptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(tdeg, 0, out=rowptr[1:])
+        t.rowptr = rowptr.to(torch.int32)
+        t.dinv = self.dinv
+        # long-row chunk list, same rule as lgc_csr_build: rows longer than LONG_ROW are cut into CHUNK-sized chunks
+        nch = torch.where(tdeg > LONG_ROW, (tdeg + CHUNK - 1) // CHUNK, torch.zeros_like(tdeg))
+        base = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(nch, 0, out=base[1:])
+        t.row_chunk_base = base.to(torch.int32)
+        t.n_chunks = int(base[-1])
+        crow = torch.repeat_interleave(torch.arange(n, device=dev, dtype=torch.int64), nch)
+        within = torch.arange(t.n_chunks, device=dev, dtype=torch.int64) - base[:-1][crow]
+        t.chunk_row = crow.to(torch.int32) if t.n_chunks else torch.zeros(1, dtype=torch.int32, device=dev)
+        t.chunk_start = ((rowptr[:-1][crow] + within * CHUNK).to(torch.int32) if t.n_chunks
+                         else torch.zeros(1, dtype=torch.int32, device=dev))
+        t._scratch, t._orders, t._long_rows = {}, {}, {}
+        t.use_row_order = self.use_row_order
+        return t
+
     def row_order(self, row_begin: int = 0, row_end: Optional[int] = None) -> Optional[torch.Tensor]:
         """Rows of [row_begin, row_end) longest first (int32), cached per range; None when disabled."""
         if not self.use_row_order:

@@ -27,8 +27,10 @@ def graphs_for(edge_index: torch.Tensor, n_nodes: int):
         return hit[0], hit[1]
     ei = edge_index.contiguous()
     g = NormGraph(ei, n_nodes)
-    gt = NormGraph(torch.stack([ei[1], ei[0]]), n_nodes)
-    if torch.equal(g.rowptr, gt.rowptr) and torch.equal(g.colidx, gt.colidx):
+    # backward graph = structural transpose with g's own values (NOT gcn_norm of the transposed edge list, which
+    # would normalise by out-degrees); for the symmetric bipartite adjacency it is g itself
+    gt = g.transposed()
+    if torch.equal(g.rowptr, gt.rowptr) and torch.equal(g.colidx, gt.colidx) and torch.equal(g.val, gt.val):
         gt = g  # symmetric graph: A_hat^T == A_hat, share the arrays
     _CACHE[key] = (g, gt, edge_index)  # keeps the tensor alive so data_ptr cannot be recycled
     while len(_CACHE) > _CACHE_MAX:

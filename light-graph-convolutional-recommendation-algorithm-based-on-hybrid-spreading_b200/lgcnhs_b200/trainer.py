@@ -33,6 +33,10 @@ class FusedBPRTrainer:
         self.uw, self.iw = model.users_emb.weight, model.items_emb.weight
         if not self.uw.is_cuda:
             raise RuntimeError("FusedBPRTrainer: the model must live on a CUDA device (no CPU fallback)")
+        if self.D not in (32, 64):
+            # fail before the first step, not at the first evaluation: the SpMM / BPR / Adam kernels also take 128,
+            # the full-rank evaluation kernel (lgc_score_topk) takes 32 and 64
+            raise RuntimeError(f"FusedBPRTrainer: embedding_dim {self.D} not supported (32 or 64)")
         dev = self.uw.device
         self.dev = dev
         self.g, self.gt = graphs_for(train_adj_index, self.N)

@@ -58,7 +58,7 @@ def calValLoss(model: LightGCN, user_num: int, item_num: int, val_edge_index: to
     users_f, users_0, items_f, items_0 = model.forward(val_edge_index)
     r_mat = convertAdjMatrixToEdgeIndex(user_num, item_num, val_edge_index)
     u, p, n = structured_negative_sampling(r_mat, contains_neg_self_loops=False)
-    n = n.clamp_(max=item_num - 1)   # the reference indexes items with neg in [0, max(U,M)): out of range when U > M
+    # negatives are drawn from [0, max val item id + 1) (lgcnhs_b200/sampling.py): always a valid row of items_f
     E = torch.cat([users_f, items_f]).detach().contiguous()
     X0 = torch.cat([users_0, items_0]).detach().contiguous()
     loss = ops.bpr_fwd_bwd(E, X0, user_num, item_num, u.contiguous(), p.contiguous(), n.contiguous(), lambda_val)

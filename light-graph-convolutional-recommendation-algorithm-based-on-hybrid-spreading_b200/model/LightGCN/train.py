@@ -5,6 +5,7 @@ import pandas as pd
 import torch
 
 from const import cfg
+from lgcnhs_b200.sampling import check_status
 from lgcnhs_b200.trainer import FusedBPRTrainer, choose_device, safe_diversity
 from metrics.accurate import getAccurateMetrics
 from metrics.diversity import getDiversityMetrics
@@ -26,7 +27,7 @@ def getEmbeddingForBPR(model: LightGCN, user_num: int, item_num: int,
     users_f, users_0, items_f, items_0 = model.forward(train_edge_index)
     edge_index_to_use = convertAdjMatrixToEdgeIndex(user_num, item_num, train_edge_index)
     u, p, n = sampleMiniBatch(batch_size, edge_index_to_use)
-    u, p, n = u.to(device), p.to(device), n.to(device).clamp(max=item_num - 1)
+    u, p, n = u.to(device), p.to(device), n.to(device)
     return users_f[u], users_0[u], items_f[p], items_0[p], items_f[n], items_0[n]
 
 
@@ -52,11 +53,12 @@ def _run_training(model, name: str, user_num: int, item_num: int, train_edge_ind
 
     for epoch in range(epochs):
         u, p, n = sampleMiniBatch(batch_size, train_ei)
-        loss = trainer.step(u.contiguous(), p.contiguous(), n.clamp(max=item_num - 1).contiguous())
+        loss = trainer.step(u.contiguous(), p.contiguous(), n.contiguous())
         if epoch % epoch_per_eval == 0:
             model.eval()
             with torch.no_grad():
                 train_loss = round(loss[0].item(), 5)
+                check_status()    # sampler range flags of the steps since the last evaluation (no extra sync: .item() above)
                 val_loss = calValLoss(model, user_num, item_num, val_edge_index, epsilon_val)
                 recommendations = getValRecommendations(model, user_num, item_num, train_edge_index, val_edge_index, k)
                 val_precision, val_recall, val_f1, val_ndcg = getAccurateMetrics(val_user_pos_items_dict, recommendations, k)

@@ -13,7 +13,7 @@ from utils.log import logger
 from utils.wrapper import calTimes
 
 
-def getLightGCNModel(user_num: int, item_num: int, rating_df: pd.DataFrame, train_data_df: pd.DataFrame,
+def getLightGCNOptiModel(user_num: int, item_num: int, rating_df: pd.DataFrame, train_data_df: pd.DataFrame,
                      val_data_df: pd.DataFrame, test_data_df: pd.DataFrame, user_features_df: pd.DataFrame,
                      item_features_df: pd.DataFrame, k: int) -> tuple:
     """(model, edge_index, train_adj, val_adj, test_adj) — reference model.py:25-94."""
@@ -28,12 +28,15 @@ def getLightGCNModel(user_num: int, item_num: int, rating_df: pd.DataFrame, trai
     return model, edge_index, train_edge_index, val_edge_index, test_edge_index
 
 
+getLightGCNModel = getLightGCNOptiModel   # round-1 name of this drop-in, kept as an alias
+
+
 @calTimes(logger, "分配权重矩阵计算完成")
 def getAllocateMat(user_num: int, item_num: int, rating_df: pd.DataFrame, train_data_df: pd.DataFrame,
                    val_data_df: pd.DataFrame, test_data_df: pd.DataFrame, user_features_df: pd.DataFrame,
                    item_features_df: pd.DataFrame, k: int) -> np.ndarray:
     """reference model.py:97-169."""
-    model = getLightGCNModel(user_num, item_num, rating_df, train_data_df, val_data_df, test_data_df,
+    model = getLightGCNOptiModel(user_num, item_num, rating_df, train_data_df, val_data_df, test_data_df,
                              user_features_df, item_features_df, k)[0]
     return fusion.allocate_score_device(model, user_num, item_num, train_data_df, val_data_df).cpu().numpy()
 
@@ -50,6 +53,6 @@ def getResourceMat(user_num: int, item_num: int, rating_df: pd.DataFrame, train_
     """F_new = G * F (reference model.py:191-243)."""
     k = cfg.RECOMMEND["k"]
     lambda_val = cfg.MODEL["HyperParameter"]["lambda"]
-    model = getLightGCNModel(user_num, item_num, rating_df, train_data_df, val_data_df, test_data_df,
+    model = getLightGCNOptiModel(user_num, item_num, rating_df, train_data_df, val_data_df, test_data_df,
                              user_features_df, item_features_df, k)[0]
     return fusion.resource_mat_host(model, user_num, item_num, train_data_df, val_data_df, lambda_val)

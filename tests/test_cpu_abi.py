@@ -44,6 +44,20 @@ def test_no_cpu_fallback():
         NormGraph(torch.zeros((2, 4), dtype=torch.int64), 4)
     with pytest.raises(RuntimeError):
         lightgcn_forward(torch.zeros(2, 64), torch.zeros(2, 64), torch.zeros((2, 4), dtype=torch.int64), 3)
+    if not torch.cuda.is_available():
+        # the metrics drop-in (consumer of the top-k lists) has no host implementation either
+        import _stub_const
+        import numpy as np
+
+        _stub_const.install()
+        from metrics.accurate import getAccurateMetrics
+        from metrics.diversity import getDiversityMetrics
+
+        rec = torch.zeros((2, 3), dtype=torch.long)
+        with pytest.raises(RuntimeError):
+            getAccurateMetrics({0: [1]}, rec, 3)
+        with pytest.raises(RuntimeError):
+            getDiversityMetrics(rec, {0: 1}, np.zeros((2, 4)), 3)
 
 
 def test_product_path_never_imports_the_oracle():
