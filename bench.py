@@ -155,6 +155,12 @@ def train_adj(d):
     return bipartite_adj(d.n_users, d.users[tr], d.items[tr]), (tr, va, te)
 
 
+def bipartite(d, idx):
+    from lgcnhs_b200.synth import bipartite_adj
+
+    return bipartite_adj(d.n_users, d.users[idx], d.items[idx])
+
+
 def prop_bytes(nnz: int, n: int, layers: int = K_LAYERS, dim: int = DIM) -> int:
     return layers * (nnz * (4 + 4 + 4 * dim) + n * (4 * dim + 4) + 4)
 

@@ -20,7 +20,7 @@ from .recommend_common import cuda_device, interactions_from_frames
 
 def find_lambda(user_num: int, item_num: int, train_data_df: pd.DataFrame, val_data_df: pd.DataFrame,
                 test_data_df: pd.DataFrame, k: int, model=None, lambdas: Optional[Sequence[float]] = None,
-                save_dir: Optional[str] = None) -> pd.DataFrame:
+                save_dir: Optional[str] = None, lists_out: Optional[list] = None) -> pd.DataFrame:
     """DataFrame(lambda, precision, recall, f1, ndcg, H, I) over the lambda grid (default np.arange(0, 1.01, 0.01),
     findLambda.py:83).  `model` (a trained LightGCN / LightGCNOpti module) selects the fusion recommender
     SpreadLightGCN(Opti) as in findLambda.py:79-98; None sweeps plain HybridS (the commented-out alternative, :100)."""
@@ -35,7 +35,7 @@ def find_lambda(user_num: int, item_num: int, train_data_df: pd.DataFrame, val_d
         model = model.to(dev)
         layer0 = (model.users_emb.weight.detach().contiguous(), model.items_emb.weight.detach().contiguous(),
                   ops.seen_csr(u, i, user_num, item_num))
-    _, res = eng.sweep(lambdas, k, test_pos, filtered=True, layer0=layer0)
+    _, res = eng.sweep(lambdas, k, test_pos, filtered=True, layer0=layer0, lists_out=lists_out)
     frame = pd.DataFrame({"lambda": lambdas, **{c: [m[c] for m in res] for c in ("precision", "recall", "f1", "ndcg", "H", "I")}})
     if save_dir is not None:
         frame.to_csv(save_dir + "lambda_evaluation_" + str(k) + ".csv", index=False)

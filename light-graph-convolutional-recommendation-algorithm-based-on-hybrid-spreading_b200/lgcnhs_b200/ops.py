@@ -524,13 +524,15 @@ class SpreadingEngine:
         return self.C
 
     def sweep(self, lambdas, k: int, test_pos: Optional[tuple] = None, filtered: bool = True,
-              gscore: Optional[torch.Tensor] = None, diversity: bool = True, layer0: Optional[tuple] = None):
+              gscore: Optional[torch.Tensor] = None, diversity: bool = True, layer0: Optional[tuple] = None,
+              lists_out: Optional[list] = None):
         """The findLambda.py:83-116 loop on the device: G once, then per lambda  HybridS -> A.W [-> * G_score] ->
         filtered top-k -> six metric sums, with no host round trip inside the loop.  The fusion factor G_score
         (getAllocateMat) is either a dense (U, M) matrix `gscore` or, better, `layer0 = (Xu, Xi, seen_csr)`: the
         layer-0 score tiles are then recomputed and multiplied with F inside lgc_score_topk and G_score is never
         materialised.  Returns (sums float64 (n_lambda, 6) on the HOST after ONE device->host copy, list of
-        per-lambda metric dicts)."""
+        per-lambda metric dicts).  `lists_out` (a list) receives the per-lambda (U, k) id tensors (device) — the
+        parity tests check them against the oracle."""
         if self.G is None:
             self.general_w()
         cooc = self.cooccurrence() if diversity else None
@@ -547,6 +549,8 @@ class SpreadingEngine:
             else:
                 idx, _ = self.recommend(lam, k, filtered=filtered, gscore=gscore, F_out=F)
             topk_metrics(idx, self.M, test_pos, cooc, deg, out=sums[n])
+            if lists_out is not None:
+                lists_out.append(idx)
         host = sums.cpu()
         return host, [metrics_from_sums(host[n].tolist(), self.U, k) for n in range(len(lambdas))]
 

@@ -110,6 +110,62 @@ def main():
                         grad_users=model.users_emb.weight.grad.numpy(), grad_items=model.items_emb.weight.grad.numpy(),
                         sample_u=su.numpy(), sample_p=sp.numpy(), sample_n=sn.numpy())
 
+    # ------------------------------------------------------------------ config 3: LightGCNOpti + SpreadLightGCNOpti
+    # The reference's own model/LightGCNOpti/model.py and model/SpreadLightGCNOpti/{model,recommend}.py, run as
+    # they are on the stub.  The pickled module the reference loads (<k>_LightGCNOpti.pth) is a seeded, untrained
+    # LightGCNOpti of the reference's own class; torch.load is given weights_only=False (torch >= 2.6 default
+    # changed; the reference's environment.yaml pins an older torch) — nothing of the reference's logic is altered.
+    from model.LightGCNOpti import model as ref_opti_model
+    from model.SpreadLightGCNOpti import model as ref_slo_model, recommend as ref_slo_rec
+    assert ref_opti_model.__file__.startswith(REF) and ref_slo_model.__file__.startswith(REF)
+    d = synth_shape("tiny")
+    tr, va, te = d.split()
+    k, lam = 10, 0.3
+    frng = np.random.default_rng(11)
+    FU, FI = 29, 31                                   # ML-100K-like feature widths
+    user_feat = np.round(frng.random((d.n_users, FU)), 3) * (frng.random((d.n_users, FU)) < 0.4)
+    item_feat = np.round(frng.random((d.n_items, FI)), 3) * (frng.random((d.n_items, FI)) < 0.4)
+    perm_u, perm_i = frng.permutation(d.n_users), frng.permutation(d.n_items)      # files are not sorted by id
+    ufd = pd.DataFrame({"user_id": perm_u, "user_features": [str(user_feat[u].tolist()) for u in perm_u]})
+    ifd = pd.DataFrame({"item_id": perm_i, "item_features": [str(item_feat[i].tolist()) for i in perm_i]})
+    df = lambda idx: pd.DataFrame({"user_id": d.users[idx], "item_id": d.items[idx], "rating": 5,  # noqa: E731
+                                   "rating_time": "2024-01-01 00:00:00"})
+    rating_df, train_df, val_df, test_df = df(np.arange(d.users.size)), df(tr), df(va), df(te)
+    torch.manual_seed(42)                             # reference LightGCNOpti/train.py:94 seeds before the constructor
+    opti = ref_opti_model.LightGCNOpti(d.n_users, d.n_items, 64, 3, torch.from_numpy(user_feat).float(),
+                                       torch.from_numpy(item_feat).float())
+    adj = ref_graph.convertEdgeIndexToAdjMatrix(d.n_users, d.n_items, torch.from_numpy(np.stack([d.users[tr], d.items[tr]])))
+    ouf, ou0, oitf, oi0 = opti.forward(adj)
+    chk_u, _, chk_i, _ = LO.lightgcn_forward(opti.users_emb.weight, opti.items_emb.weight, adj, 3)
+    assert torch.equal(ouf, chk_u) and torch.equal(oitf, chk_i)
+    const.cfg.RECOMMEND["k"] = k
+    const.cfg.MODEL["name"] = "SpreadLightGCNOpti"
+    const.cfg.MODEL["HyperParameter"]["lambda"] = lam
+    torch.save(opti, const.cfg.MODEL["save_path"] + str(k) + "_LightGCNOpti.pth")
+    _load = torch.load
+    torch.load = lambda *a, **kw: _load(*a, **{**kw, "weights_only": False})
+    try:
+        Gs = ref_slo_model.getAllocateMat(d.n_users, d.n_items, rating_df, train_df, val_df, test_df, ufd, ifd, k)
+        F_new = ref_slo_model.getResourceMat(d.n_users, d.n_items, rating_df, train_df, val_df, test_df, ufd, ifd)
+        rec = ref_slo_rec.recommendSpreadLightGCNOpti(d.n_users, d.n_items, rating_df, train_df, val_df, test_df, ufd, ifd)
+    finally:
+        torch.load = _load
+    rec = np.array([rec[u] for u in range(d.n_users)], dtype=np.int64)
+    both = pd.concat([train_df, val_df])
+    A = SO.interaction_matrix(d.n_users, d.n_items, both.user_id, both.item_id)
+    e_tr = torch.from_numpy(np.stack([d.users[tr], d.items[tr]]))
+    e_va = torch.from_numpy(np.stack([d.users[va], d.items[va]]))
+    oGs = LO.masked_score(opti.users_emb.weight.detach(), opti.items_emb.weight.detach(), e_tr, e_va).numpy()
+    oF = SO.fused_resource(oGs, SO.get_resource(A, SO.hybrids(A, SO.get_spreading_general_mat(A), lam)))
+    assert np.array_equal(Gs, oGs) and np.array_equal(F_new, oF)                 # oracle == reference, bit for bit
+    loop = SO.recommend_loop(F_new, ref_trans.getUserItemsDictByDataframe(both), k)
+    assert all(np.array_equal(rec[u], np.asarray(loop[u])) for u in range(d.n_users))
+    np.savez_compressed(os.path.join(OUT, "opti_tiny.npz"), users=d.users, items=d.items, train=tr, val=va, test=te,
+                        user_feat=user_feat, item_feat=item_feat, perm_u=perm_u, perm_i=perm_i,
+                        users_w=opti.users_emb.weight.detach().numpy(), items_w=opti.items_emb.weight.detach().numpy(),
+                        users_final=ouf.detach().numpy(), items_final=oitf.detach().numpy(), adj=adj.numpy(),
+                        G_score=Gs, F_new=F_new, rec=rec, k=np.array(k), lam=np.array(lam))
+
     # ------------------------------------------------------------------ formats + metrics
     d = synth_shape("small")
     tr, va, te = d.split()

@@ -212,3 +212,129 @@ def test_fusion_recommend_matches_oracle(dev):
     fi, fv = SO.recommend_fast(Fn, A, 10)
     got = np.array([out[u] for u in range(d.n_users)])
     assert np.allclose(np.take_along_axis(Fn, got, 1), fv, rtol=1e-4, atol=1e-6 * np.abs(Fn).max())
+
+
+def test_get_embedding_for_bpr_matches_oracle(dev, monkeypatch):
+    """P4 getEmbeddingForBPR (reference train.py:26-59): forward + six row gathers, with the mini-batch injected so
+    both sides use the same (u, pos, neg); loss and gradients through the six tensors vs autograd on the oracle."""
+    _stub_const.install()
+    import model.LightGCN.train as T
+    from lgcnhs_b200.synth import bipartite_adj
+    from model.LightGCN.loss import BPRLoss
+    from model.LightGCN.model import LightGCN
+
+    d, *_, (tr, va, te) = _frames("small")
+    adj = torch.from_numpy(bipartite_adj(d.n_users, d.users[tr], d.items[tr]))
+    g = torch.Generator().manual_seed(3)
+    B = 256
+    rows = torch.randint(tr.size, (B,), generator=g)
+    u = torch.from_numpy(d.users[tr])[rows]
+    p = torch.from_numpy(d.items[tr])[rows]
+    n = torch.randint(d.n_items, (B,), generator=g)
+    seen = {}
+    monkeypatch.setattr(T, "sampleMiniBatch", lambda bs, ei: (seen.setdefault("ei", ei), (u.to(dev), p.to(dev), n.to(dev)))[1])
+    torch.manual_seed(42)
+    m = LightGCN(d.n_users, d.n_items, 64, 3)
+    uw = m.users_emb.weight.detach().clone().requires_grad_()
+    iw = m.items_emb.weight.detach().clone().requires_grad_()
+    m = m.to(dev)
+    six = T.getEmbeddingForBPR(m, d.n_users, d.n_items, adj.to(dev), B, dev)
+    # the sampler was handed the (2, E) user->item edge list recovered from the adjacency (train.py:48)
+    assert torch.equal(seen["ei"].cpu(), LO.convert_adj_to_edge_index(d.n_users, d.n_items, adj))
+    ouf, ou0, oif, oi0 = LO.lightgcn_forward(uw, iw, adj, 3)
+    ref6 = (ouf[u], ou0[u], oif[p], oi0[p], oif[n], oi0[n])
+    assert len(six) == 6
+    for got, ref, nm in zip(six, ref6, ("u_f", "u_0", "p_f", "p_0", "n_f", "n_0")):
+        assert got.shape == (B, 64)
+        assert_close(got, ref.detach(), f"getEmbeddingForBPR {nm}")
+    loss = BPRLoss(*six, 1e-4)
+    ref_loss = LO.bpr_loss(*ref6, 1e-4)
+    assert abs(loss.item() - ref_loss.item()) <= 1e-5 * abs(ref_loss.item()) + 1e-7
+    loss.backward()
+    ref_loss.backward()
+    assert_close(m.users_emb.weight.grad, uw.grad, "P4 dL/d users", sum_abs=uw.grad.abs() + 1e-6)
+    assert_close(m.items_emb.weight.grad, iw.grad, "P4 dL/d items", sum_abs=iw.grad.abs() + 1e-6)
+
+
+def test_cal_val_loss_matches_oracle(dev, monkeypatch):
+    """P9 calValLoss (reference evaluation.py:56-86): propagate over the VAL graph, BPR over ALL val edges with the
+    negatives injected, rounded to 5 decimals."""
+    _stub_const.install()
+    import model.LightGCN.evaluation as E
+    from lgcnhs_b200.synth import bipartite_adj
+    from model.LightGCN.model import LightGCN
+
+    d, *_, (tr, va, te) = _frames("small")
+    val_adj = torch.from_numpy(bipartite_adj(d.n_users, d.users[va], d.items[va]))
+    r_mat = LO.convert_adj_to_edge_index(d.n_users, d.n_items, val_adj)          # (2, E_val) user -> item
+    g = torch.Generator().manual_seed(5)
+    neg = torch.randint(d.n_items, (r_mat.shape[1],), generator=g)
+    calls = {}
+
+    def fake_sampler(edge_index, contains_neg_self_loops=True, **kw):
+        calls["loops"] = contains_neg_self_loops
+        assert torch.equal(edge_index.cpu(), r_mat)
+        return edge_index[0], edge_index[1], neg.to(edge_index.device)
+
+    monkeypatch.setattr(E, "structured_negative_sampling", fake_sampler)
+    torch.manual_seed(42)
+    m = LightGCN(d.n_users, d.n_items, 64, 3)
+    uw, iw = m.users_emb.weight.detach().clone(), m.items_emb.weight.detach().clone()
+    m = m.to(dev)
+    for eps in (1e-6, 1e-3):
+        got = E.calValLoss(m, d.n_users, d.n_items, val_adj.to(dev), eps)
+        uf, u0, itf, i0 = LO.lightgcn_forward(uw, iw, val_adj, 3)
+        u, p = r_mat[0], r_mat[1]
+        ref = round(LO.bpr_loss(uf[u], u0[u], itf[p], i0[p], itf[neg], i0[neg], eps).item(), 5)
+        assert isinstance(got, float) and abs(got - ref) <= 1e-5 + 1e-5 * abs(ref), (got, ref)
+    assert calls["loops"] is False                                                # evaluation.py:72
+    # and with the real device sampler: finite, negatives valid (never a positive of the user, never the user id)
+    monkeypatch.undo()
+    from lgcnhs_b200.sampling import check_status, structured_negative_sampling
+    uu, pp, nn_ = structured_negative_sampling(r_mat.to(dev), contains_neg_self_loops=False)
+    check_status()
+    pos = set(zip(r_mat[0].tolist(), r_mat[1].tolist()))
+    assert all((a, b) not in pos and a != b for a, b in zip(uu.tolist(), nn_.tolist()))
+    assert int(nn_.max()) <= int(r_mat[1].max()) and int(nn_.min()) >= 0          # drawn inside the item-id range
+    assert np.isfinite(E.calValLoss(m, d.n_users, d.n_items, val_adj.to(dev), 1e-6))
+
+
+def test_negative_range_is_items_even_when_users_outnumber_items(dev):
+    """with U > M (ML-1M / ML-20M shapes) negatives must be spread over the items, not clamped onto the
+    last one; with U < M the draw range equals the reference's max-id + 1."""
+    _stub_const.install()
+    from lgcnhs_b200.sampling import check_status
+    from model.LightGCN.loss import sampleMiniBatch
+
+    g = np.random.default_rng(0)
+    U, M, E = 500, 40, 4000
+    ei = torch.from_numpy(np.unique(np.stack([g.integers(0, U, E), g.integers(0, M, E)]), axis=1)).to(dev)
+    torch.manual_seed(1)
+    u, p, n = sampleMiniBatch(20000, ei)
+    check_status()
+    assert int(n.max()) < M and int(n.min()) >= 0
+    cnt = torch.bincount(n, minlength=M).float()
+    assert cnt.max() < 3.0 * cnt.mean()                      # no pile-up on one item (was ~81% at the ML-20M shape)
+    pos = set(zip(ei[0].tolist(), ei[1].tolist()))
+    assert not any((a, b) in pos for a, b in zip(u.tolist(), n.tolist()))
+
+
+def test_heats_douban_branch_matches_oracle(dev):
+    """S5 dispatch quirk: HeatS on the douban dataset runs HybridS with lambda = 0.99 on the TRANSPOSED general
+    matrix (reference SpreadMethod/recommend.py:99-101)."""
+    cfg = _stub_const.install(model="HeatS", dataset="douban", lam=0.5, k=10)
+    from model.SpreadMethod.recommend import recommendSpreadMethod
+
+    d, rating, train_df, val_df, test_df, _ = _frames("tiny")
+    out = recommendSpreadMethod(d.n_users, d.n_items, train_df, val_df, "HeatS")
+    both = pd.concat([train_df, val_df])
+    A = SO.interaction_matrix(d.n_users, d.n_items, both.user_id, both.item_id)
+    Gm = SO.get_spreading_general_mat(A)
+    F = SO.get_resource(A, SO.hybrids(A, Gm.T, 0.99))                             # recommend.py:100-101
+    ref_idx, _ = SO.recommend_fast(F, A, 10)
+    from _parity import assert_topk_parity
+    got = np.array([out[u] for u in range(d.n_users)])
+    assert_topk_parity(got, ref_idx, F, "HeatS@douban", seen_mask=A > 0, min_checked=0.5)
+    # and it is NOT what lambda = 0.5 (the cfg value) or plain HeatS (lambda = 0) would give
+    F0 = SO.get_resource(A, SO.hybrids(A, Gm, 0.0))
+    assert not np.array_equal(SO.recommend_fast(F0, A, 10)[0], got)

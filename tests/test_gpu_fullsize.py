@@ -1,6 +1,7 @@
-"""GPU parity at BASELINE.json's FULL sizes through size-independent properties (the CPU oracle cannot
-run these shapes in seconds): known answers, symmetry, linearity, conservation laws and selection
-invariants that follow from the reference's formulas.
+"""GPU parity at BASELINE.json's FULL sizes: (1) DIRECT comparison with the CPU oracle — it runs one propagation
+layer of the ML-20M graph in ~1.5 s and the whole ML-1M spreading pipeline in < 1 s on the box's host cores — and
+(2) size-independent properties: known answers, symmetry, linearity, conservation laws and selection invariants
+that follow from the reference's formulas.
 
 Shapes: propagation on the ML-20M-shape train graph (config 5, nnz = 32 M) and Amazon-Book shape
 (config 4); spreading + top-20 on the ML-1M shape (config 2); fused LightGCN score/top-k on the
@@ -137,3 +138,137 @@ def test_lightgcn_score_topk_amazon_book(dev):
     got_v = torch.gather(score, 1, rec[us])
     assert torch.allclose(got_v, rv, rtol=1e-5, atol=1e-6)            # score at rank
     assert (rec[us] == ri).float().mean() > 0.999                     # ids identical except at float ties
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# direct oracle comparisons at full size
+# ------------------------------------------------------------------------------------------------------------------
+def _row_tolerance(adj_np, x_abs, n, ref):
+    """Tolerance for one SpMM output at full size.  Base: 1e-5 |ref| + 1e-7 max|ref|.  A hub row sums
+    up to ~1e5 signed terms: the CPU reference accumulates them sequentially in fp32 (error ~ sqrt(deg) u sum|terms|
+    typically, (deg-1) u sum|terms| worst case) while the device sums in a tree, so two CORRECT fp32 results differ by
+    a multiple of u * sum|terms| that grows with the row length; sum|terms| = (|A_hat| |X|)[row] is evaluated in
+    float64.  The device is additionally held to the tight bound against the float64 result (see the callers)."""
+    import scipy.sparse as sp
+
+    deg = np.bincount(adj_np[1], minlength=n).astype(np.float64)
+    dinv = np.where(deg > 0, 1.0 / np.sqrt(np.maximum(deg, 1)), 0.0)
+    A = sp.csr_matrix((dinv[adj_np[0]] * dinv[adj_np[1]], (adj_np[1], adj_np[0])), shape=(n, n))
+    sum_abs = A @ x_abs
+    base = 1e-5 * np.abs(ref) + 1e-7 * np.abs(ref).max()
+    return A, sum_abs, deg, base
+
+
+@pytest.mark.parametrize("shape", ["amazon-book", "ml-20m"])
+def test_propagation_fullsize_vs_oracle(dev, shape):
+    """One LO.propagate layer and the 3-layer mean of LO.lightgcn_forward (the PyG-equivalent restatement of
+    model/LightGCN/model.py:53-72) on the full train graph vs the fused CUDA path."""
+    import bench
+    from lgcnhs_b200 import ops
+    from oracle import lightgcn_oracle as LO
+
+    d = bench.load_shape(shape)
+    adj_np, _ = bench.train_adj(d)
+    n = d.n_users + d.n_items
+    adj = torch.from_numpy(adj_np)
+    torch.manual_seed(42)
+    x0 = torch.empty(n, 64).normal_(std=0.1)
+    g = ops.NormGraph(adj.to(dev), n)
+    # --- CSR / gcn_norm: bit-exact integer work and fp32 values
+    ei, norm = LO.gcn_norm(adj)
+    order = np.lexsort((adj_np[0], adj_np[1]))
+    assert np.array_equal(g.colidx.cpu().numpy()[: adj_np.shape[1]], adj_np[0][order].astype(np.int32))
+    assert np.array_equal(g.val.cpu().numpy()[: adj_np.shape[1]], norm.numpy()[order])
+    # --- one layer
+    ref1 = LO.propagate(ei, x0, norm).numpy().astype(np.float64)
+    got1 = g.spmm(x0.to(dev)).cpu().numpy().astype(np.float64)
+    A, sum_abs, deg, base = _row_tolerance(adj_np, x0.abs().numpy().astype(np.float64), n, ref1)
+    u = 2.0 ** -24
+    tol = base + (8 + 4 * np.sqrt(deg))[:, None] * u * sum_abs
+    bad = np.abs(got1 - ref1) > tol
+    assert not bad.any(), f"{shape} layer vs oracle: {int(bad.sum())} entries out, max err {np.abs(got1 - ref1).max():.3e}"
+    exact1 = A @ x0.numpy().astype(np.float64)
+    tight = 1e-5 * np.abs(exact1) + 1e-7 * np.abs(exact1).max() + (8 + 2 * np.log2(np.maximum(deg, 2)))[:, None] * u * sum_abs
+    bad = np.abs(got1 - exact1) > tight
+    assert not bad.any(), f"{shape} layer vs float64: {int(bad.sum())} entries out, max err {np.abs(got1 - exact1).max():.3e}"
+    # the norm-wise statement of the tolerance (SURVEY 8d): ||x - ref||_inf <= 1e-5 ||ref||_inf
+    assert np.abs(got1 - ref1).max() <= 1e-5 * np.abs(ref1).max()
+    del ref1, got1
+    # --- K = 3 layers + mean through the module-level call
+    uf, _, itf, _ = LO.lightgcn_forward(x0[: d.n_users], x0[d.n_users:], adj, 3)
+    ref = torch.cat([uf, itf]).numpy().astype(np.float64)
+    got = g.propagate_mean(x0.to(dev), 3).cpu().numpy().astype(np.float64)
+    e1 = A @ x0.numpy().astype(np.float64)
+    e2 = A @ e1
+    e3 = A @ e2
+    exact = (x0.numpy().astype(np.float64) + e1 + e2 + e3) / 4
+    sa1 = A @ np.abs(x0.numpy().astype(np.float64))
+    sa = (np.abs(x0.numpy()) + sa1 + A @ np.abs(e1) + A @ np.abs(e2)) / 4       # scale of the summed terms per entry
+    tol = 1e-5 * np.abs(ref) + 1e-7 * np.abs(ref).max() + (8 + 4 * np.sqrt(deg))[:, None] * u * sa
+    bad = np.abs(got - ref) > tol
+    assert not bad.any(), f"{shape} 3-layer mean vs oracle: {int(bad.sum())} out, max err {np.abs(got - ref).max():.3e}"
+    assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
+    assert np.abs(got - exact).max() <= np.abs(ref - exact).max() * 2 + 1e-7 * np.abs(exact).max()   # no farther from float64 than the CPU reference
+
+
+def test_spreading_ml1m_vs_oracle(dev):
+    """BASELINE config 2 at full size against the reference's NumPy float64 formulas (oracle): G, HybridS, F = A.W
+    and the filtered top-20 for lambda in {0, 0.37, 1}."""
+    import bench
+    from _parity import assert_close_np, assert_topk_parity
+    from lgcnhs_b200 import ops
+    from oracle import spread_oracle as SO
+
+    d = bench.load_shape("ml-1m")
+    tr, va, _ = d.split()
+    sel = np.concatenate([tr, va])
+    U, M = d.n_users, d.n_items
+    eng = ops.SpreadingEngine(U, M, torch.from_numpy(d.users[sel]).to(dev), torch.from_numpy(d.items[sel]).to(dev))
+    A = SO.interaction_matrix(U, M, d.users[sel], d.items[sel])
+    Gm = SO.get_spreading_general_mat(A)
+    assert_close_np(eng.general_w().cpu().numpy(), Gm, "G = A^T K_u^-1 A at ML-1M vs oracle")
+    assert np.array_equal(eng.ku.cpu().numpy(), A.sum(1).astype(np.int32))
+    assert np.array_equal(eng.ki.cpu().numpy(), A.sum(0).astype(np.int32))
+    for lam in (0.0, 0.37, 1.0):
+        W = SO.hybrids(A, Gm, lam)
+        F = SO.get_resource(A, W)
+        Wd = eng.scale(lam, want_w32=True)
+        assert_close_np(Wd.cpu().numpy(), W, f"HybridS({lam}) at ML-1M vs oracle")
+        Fd = eng.resource()
+        assert_close_np(Fd.cpu().numpy(), F, f"F = A.W ({lam}) at ML-1M vs oracle")
+        idx, _ = eng.recommend(lam, 20)
+        ref_idx, _ = SO.recommend_fast(F, A, 20)
+        assert_topk_parity(idx.cpu().numpy(), ref_idx, F, f"top-20 ({lam}) at ML-1M vs oracle", seen_mask=A > 0,
+                           min_checked=0.9)
+
+
+def test_lightgcn_eval_amazon_book_vs_oracle(dev):
+    """Full-rank eval of config 4 against the CPU oracle (LO.masked_score + torch.topk, recommend.py:86-114) on a
+    sample of users (the oracle materialises U_s x 91 599 scores)."""
+    import bench
+    import _stub_const
+    from _parity import assert_topk_parity
+    from oracle import lightgcn_oracle as LO
+
+    _stub_const.install()
+    from model.LightGCN.evaluation import getValRecommendations
+    from model.LightGCN.model import LightGCN
+
+    d = bench.load_shape("amazon-book")
+    adj_np, (tr, va, te) = bench.train_adj(d)
+    torch.manual_seed(42)
+    m = LightGCN(d.n_users, d.n_items, 64, 3)
+    uw, iw = m.users_emb.weight.detach().clone(), m.items_emb.weight.detach().clone()
+    m = m.to(dev)
+    adj = torch.from_numpy(adj_np).to(dev)
+    val_adj = torch.from_numpy(bench.bipartite(d, va)).to(dev)
+    rec = getValRecommendations(m, d.n_users, d.n_items, adj, val_adj, 20).cpu().numpy()     # masks TRAIN pairs only
+    us = np.arange(0, d.n_users, 97)
+    remap = -np.ones(d.n_users, dtype=np.int64)
+    remap[us] = np.arange(us.size)
+    keep = remap[d.users[tr]] >= 0
+    e_tr = torch.from_numpy(np.stack([remap[d.users[tr][keep]], d.items[tr][keep]]))
+    score = LO.masked_score(uw[us], iw, e_tr)
+    rv, ri = LO.topk_items(score, 20)
+    # masked pairs stay IN the ranking at -1024 (reference quirk), so there is no exclusion mask to pass
+    assert_topk_parity(rec[us], ri.numpy(), score.numpy(), "amazon-book eval vs oracle", min_checked=0.95)

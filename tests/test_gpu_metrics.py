@@ -46,7 +46,7 @@ def test_metrics_duplicates_and_padding(dev):
     import _stub_const
 
     _stub_const.install()
-    import metrics.diversity as D
+    import _metrics_numpy as MN
     from lgcnhs_b200 import ops
     U, M, k = 40, 60, 6
     g = np.random.default_rng(5)
@@ -57,8 +57,8 @@ def test_metrics_duplicates_and_padding(dev):
     rec[3, 4] = rec[3, 1]           # duplicate inside a list
     A = S.interaction_matrix(U, M, users, items)
     deg = {i: int(c) for i, c in enumerate(A.sum(0)) if c > 0}
-    H_ref = D.calHammingDistance(rec, k)
-    I_ref = D.calInternalSimilarity(rec, deg, A, k)
+    H_ref = MN.hamming_distance(rec.numpy(), k)
+    I_ref = MN.internal_similarity(rec.numpy(), deg, A, k)
     sums = ops.topk_metrics(rec.to(dev).contiguous(), M, None, eng.cooccurrence(), eng.ki).cpu()
     m = ops.metrics_from_sums(sums.tolist(), U, k)
     assert abs(m["H"] - H_ref) <= 1e-5 and abs(m["I"] - I_ref) <= 1e-5
@@ -69,10 +69,10 @@ def test_lambda_sweep_matches_per_lambda_oracle(dev):
     import _stub_const
 
     _stub_const.install()
+    import _metrics_numpy as MN
+    from _parity import assert_topk_parity
     from lgcnhs_b200 import ops
     from lgcnhs_b200.synth import synth_shape
-    from metrics.accurate import getAccurateMetrics
-    from metrics.diversity import getDiversityMetrics
 
     d = synth_shape("small")
     tr, va, te = d.split()
@@ -81,22 +81,31 @@ def test_lambda_sweep_matches_per_lambda_oracle(dev):
     eng = _engine(dev, U, M, d.users[tv], d.items[tv])
     pos = ops.seen_csr(torch.from_numpy(d.users[te]).to(dev), torch.from_numpy(d.items[te]).to(dev), U, M)
     lams = [0.0, 0.3, 0.85, 1.0]
-    _, res = eng.sweep(lams, k, pos)
+    lists = []
+    _, res = eng.sweep(lams, k, pos, lists_out=lists)
     A = S.interaction_matrix(U, M, d.users[tv], d.items[tv])
     Gm = S.get_spreading_general_mat(A)
     test_dict = {}
     for u, i in zip(d.users[te].tolist(), d.items[te].tolist()):
         test_dict.setdefault(u, []).append(i)
     deg = {i: int(c) for i, c in enumerate(A.sum(0)) if c > 0}
-    for lam, m in zip(lams, res):
+    for lam, m, dev_idx in zip(lams, res, lists):
         F = S.get_resource(A, S.hybrids(A, Gm, lam))
         idx, _ = S.recommend_fast(F, A, k)
-        rec = torch.from_numpy(idx.astype(np.int64))
-        p, r, f1, n = getAccurateMetrics(test_dict, rec, k)
-        H, I = getDiversityMetrics(rec, deg, A, k)
+        # (1) the lists: identical to the oracle's except at float ties (tie-aware, score at rank always checked)
+        got_idx = dev_idx.cpu().numpy()
+        assert_topk_parity(got_idx, idx, F, f"sweep lists lambda={lam}", seen_mask=A > 0, min_checked=0.8)
+        # (2) the six metrics of exactly those lists, evaluated independently in NumPy (the reference's formulas,
+        #     pinned to the reference's outputs in test_cpu_host_logic.py): +-1e-5 after the 5-dp rounding
+        p, r, f1, n = MN.accurate_metrics(test_dict, got_idx, k)
+        H, I = MN.diversity_metrics(got_idx, deg, A, k)
         got = [m["precision"], m["recall"], m["f1"], m["ndcg"], m["H"], m["I"]]
-        # ids can differ at float ties between the fp64 oracle and the fp32 device scores: 2e-4 covers one swapped hit
-        assert np.allclose(got, [p, r, f1, n, H, I], atol=2e-4), (lam, got, [p, r, f1, n, H, I])
+        assert np.allclose(got, [p, r, f1, n, H, I], atol=1e-5), (lam, got, [p, r, f1, n, H, I])
+        # (3) and the oracle's own lists give the same metrics wherever no tie was involved in the difference
+        same = (got_idx == idx).all()
+        if same:
+            po, ro, f1o, no = MN.accurate_metrics(test_dict, idx, k)
+            assert np.allclose([p, r, f1, n], [po, ro, f1o, no], atol=1e-5)
 
 
 def test_find_lambda_fusion_sweep_matches_reference_pipeline(dev, tmp_path):
@@ -106,10 +115,10 @@ def test_find_lambda_fusion_sweep_matches_reference_pipeline(dev, tmp_path):
     import pandas as pd
 
     _stub_const.install()
+    import _metrics_numpy as MN
+    from _parity import assert_topk_parity
     from lgcnhs_b200.find_lambda import find_lambda
     from lgcnhs_b200.synth import synth_shape
-    from metrics.accurate import getAccurateMetrics
-    from metrics.diversity import getDiversityMetrics
     from model.LightGCN.model import LightGCN
     from oracle import lightgcn_oracle as LO
 
@@ -120,7 +129,9 @@ def test_find_lambda_fusion_sweep_matches_reference_pipeline(dev, tmp_path):
     torch.manual_seed(42)
     model = LightGCN(U, M, 64, 3)
     lams = [0.0, 0.5, 1.0]
-    frame = find_lambda(U, M, df(tr), df(va), df(te), k, model=model, lambdas=lams, save_dir=str(tmp_path) + "/")
+    lists = []
+    frame = find_lambda(U, M, df(tr), df(va), df(te), k, model=model, lambdas=lams, save_dir=str(tmp_path) + "/",
+                        lists_out=lists)
     assert list(frame.columns) == ["lambda", "precision", "recall", "f1", "ndcg", "H", "I"]
     assert (tmp_path / f"lambda_evaluation_{k}.csv").exists()
     tv = np.r_[tr, va]
@@ -136,9 +147,40 @@ def test_find_lambda_fusion_sweep_matches_reference_pipeline(dev, tmp_path):
     for n, lam in enumerate(lams):
         F_new = S.fused_resource(Gs, S.get_resource(A, S.hybrids(A, Gm, lam)))
         idx, _ = S.recommend_fast(F_new, A, k)
-        rec = torch.from_numpy(idx.astype(np.int64))
-        p, r, f1, nd = getAccurateMetrics(test_dict, rec, k)
-        H, I = getDiversityMetrics(rec, deg, A, k)
+        got_idx = lists[n].cpu().numpy()
+        # lists: tie-aware against the oracle (F_new has many exact zeros and fp32-vs-fp64 near-ties)
+        assert_topk_parity(got_idx, idx, F_new, f"fusion sweep lists lambda={lam}", seen_mask=A > 0, min_checked=0.3,
+                           tol_mult=4.0)
+        # metrics: the device's numbers for its own lists vs the independent NumPy evaluation, +-1e-5
+        p, r, f1, nd = MN.accurate_metrics(test_dict, got_idx, k)
+        H, I = MN.diversity_metrics(got_idx, deg, A, k)
         got = frame.iloc[n][["precision", "recall", "f1", "ndcg", "H", "I"]].to_numpy(dtype=float)
-        # ids can differ at float ties (F_new has many exact zeros and fp32-vs-fp64 near-ties): a few swapped items
-        assert np.allclose(got, [p, r, f1, nd, H, I], atol=5e-4), (lam, got, [p, r, f1, nd, H, I])
+        assert np.allclose(got, [p, r, f1, nd, H, I], atol=1e-5), (lam, got, [p, r, f1, nd, H, I])
+
+
+def test_metrics_dropin_modules_match_reference_golden(dev):
+    """The drop-in metrics/accurate.py + metrics/diversity.py (device only, same call signatures as the reference:
+    dicts, a CPU tensor of lists, the dense float64 interaction matrix) vs the reference's recorded outputs."""
+    import _stub_const
+    import pandas as pd
+
+    _stub_const.install()
+    from metrics import accurate, diversity
+    from utils import trans
+
+    z = np.load(os.path.join(G, "metrics_small.npz"))
+    users, items = z["users"], z["items"]
+    te, tv = z["test"], np.r_[z["train"], z["val"]]
+    test_dict = trans.getUserItemsDictByDataframe(pd.DataFrame({"user_id": users[te], "item_id": items[te]}))
+    tv_dict = trans.getUserItemsDictByDataframe(pd.DataFrame({"user_id": users[tv], "item_id": items[tv]}))
+    deg = trans.getItemDegreeByUserPosItemDict(tv_dict)
+    A = trans.getInteractionMatrixByDataframe(300, 500, pd.DataFrame({"user_id": users[tv], "item_id": items[tv]}))
+    rec = torch.from_numpy(z["rec"])
+    acc = accurate.getAccurateMetrics(test_dict, rec, 10)
+    assert np.allclose(acc, z["accurate"], atol=1e-5)
+    assert np.allclose(accurate.calPrecisionAndRecall(test_dict, rec, 10), z["accurate"][:2], atol=1e-5)
+    assert abs(accurate.calNDCG(test_dict, rec, 10) - z["accurate"][3]) <= 1e-5
+    assert abs(accurate.calF1Score(acc[0], acc[1]) - z["accurate"][2]) <= 1e-5
+    assert np.allclose(diversity.getDiversityMetrics(rec, deg, A, 10), z["diversity"], atol=1e-5)
+    assert abs(diversity.calHammingDistance(rec, 10) - z["diversity"][0]) <= 1e-5
+    assert abs(diversity.calInternalSimilarity(rec, deg, A, 10) - z["diversity"][1]) <= 1e-5

@@ -127,3 +127,33 @@ def test_bad_edges_fail_loudly(dev):
         NormGraph(torch.tensor([[0, 9], [9, 0]], dtype=torch.int64, device=dev), 8)
     with pytest.raises(LgcnhsError):
         NormGraph(torch.tensor([[0, 1], [1, 0]], dtype=torch.int64), 8)  # CPU tensor: no fallback
+
+
+def test_backward_on_non_symmetric_graph_matches_autograd(dev):
+    """the backward graph must be the STRUCTURAL transpose of A_hat with the forward values; re-running
+    gcn_norm on the transposed edge list (out-degree normalisation) is only equal for symmetric graphs.  A directed
+    random graph, with a hub target so that the chunk lists of the transpose are exercised, vs autograd on the oracle."""
+    from lgcnhs_b200.propagation import PropagateMean, graphs_for
+
+    g = np.random.default_rng(2)
+    n, e = 700, 9000
+    src, dst = g.integers(0, n, e), g.integers(0, n, e)
+    src = np.r_[src, np.full(600, 5)]                  # node 5 fans OUT to 600 targets -> long row of the transpose
+    dst = np.r_[dst, g.permutation(n)[:600]]
+    key = np.unique(src * n + dst)
+    ei = torch.from_numpy(np.stack([key // n, key % n]))
+    fwd, bwd = graphs_for(ei.to(dev), n)
+    assert bwd is not fwd and bwd.n_chunks >= 1
+    torch.manual_seed(0)
+    x = torch.randn(n, 64) * 0.1
+    w = torch.randn(n, 64)
+    xr = x.clone().requires_grad_()
+    layers = O.propagate_layers(xr, ei, 3)
+    ref = sum(layers) / 4
+    (ref * w).sum().backward()
+    xd = x.to(dev).requires_grad_()
+    out = PropagateMean.apply(xd, fwd, bwd, 3)
+    assert_close(out, ref.detach(), "forward on a directed graph")
+    (out * w.to(dev)).sum().backward()
+    absA = sum(O.propagate_layers(w.abs(), torch.stack([ei[1], ei[0]]), 3)) / 4
+    assert_close(xd.grad, xr.grad, "dX0 on a directed graph", sum_abs=absA + 1e-6)
