@@ -36,11 +36,26 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 K_LAYERS, DIM = 3, 64
-# dram__bytes_read.sum + dram__bytes_write.sum per spmm_layer_kernel launch from the committed
-# `ncu --set full` capture (profiles/r1_ncu_all_kernels.txt, ml-20m train graph, mean of the 3 layers): ~compulsory
-# traffic, the
-# gathers are served by L2
-NCU_SPMM_DRAM_BYTES = {"ml-20m": 404_000_000}
+
+
+def ncu_traffic(key: str):
+    """roofline.traffic = dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel.  It cannot be
+    measured in this process (a number taken under a profiler is never a bench value), so it is read from the
+    COMMITTED capture summary profiles/ncu_traffic.json — written by tools/ncu_traffic.py from an `ncu --set full`
+    CSV kept beside it — and only if that CSV's sha256 still matches; otherwise the field is null."""
+    import hashlib
+
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            table = json.load(f)
+        ent = table[key]
+        with open(os.path.join(ROOT, "profiles", ent["source"]), "rb") as f:
+            if hashlib.sha256(f.read()).hexdigest() != ent["sha256"]:
+                return None, {"error": "profiles/%s changed since ncu_traffic.json was written" % ent["source"]}
+        return ent["dram_bytes_per_launch"], {k: ent[k] for k in ("source", "sha256", "kernel", "launches", "captured_with")
+                                              if k in ent}
+    except Exception as e:
+        return None, {"error": "no committed ncu capture for %s (%s)" % (key, type(e).__name__)}
 
 
 def peaks():
@@ -191,6 +206,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the reference arm must use the box's host cores at every N
+    # (the other ranks exit at once, so rank 0 has the whole host)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(max(1, cores))
     d = load_shape(args.shape)
     adj, _ = train_adj(d)
     steps, warmup = max(1, min(args.steps, 40)), max(0, min(args.warmup, 3))   # ~1.5 s per step on 16 cores
@@ -213,6 +232,100 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
+def install_cfg(model: str, dataset: str = "movielens", k: int = 20, lam: float = 0.3):
+    """The drop-in modules read the reference's `const.cfg` (const.py:111-190).  /root/reference is not on the GPU box,
+    so the bench installs a module of that name with the attributes the recommend* entry points read."""
+    import tempfile
+    import types
+
+    root = tempfile.mkdtemp(prefix="lgc_bench_cfg_")
+    paths = {n: os.path.join(root, n) + "/" for n in ("log", "preprocess", "recommend", "model", "evaluation", "pictures")}
+    for q in paths.values():
+        os.makedirs(q, exist_ok=True)
+    cfg = types.SimpleNamespace(
+        DATA_SET=dataset, LOG={"file_path": paths["log"]}, PREPROCESSING={"seed": 42, "save_path": paths["preprocess"]},
+        RECOMMEND={"k": k, "save_path": paths["recommend"]}, EVALUATION={"save_path": paths["evaluation"]},
+        PICTURES={"save_path": paths["pictures"]},
+        MODEL={"name": model, "save_path": paths["model"],
+               "HyperParameter": {"seed": 42, "embedding_dim": DIM, "layers": K_LAYERS, "lr": 1e-3, "gamma": 0.95, "epochs": 4,
+                                  "epoch_per_eval": 2, "epoch_per_lr_decay": 2, "batch_size": 1024, "epsilon": 1e-6,
+                                  "lambda": lam}})
+    mod = types.ModuleType("const")
+    mod.cfg = cfg
+    sys.modules["const"] = mod
+    for name in [m for m in sys.modules if m.split(".")[0] in ("model", "utils", "metrics", "processing")]:
+        del sys.modules[name]
+    return cfg
+
+
+def frames_of(d, *index_sets):
+    import pandas as pd
+
+    return [pd.DataFrame({"user_id": d.users[ix], "item_id": d.items[ix]}) for ix in index_sets]
+
+
+def wall_ms(fn, reps: int, warm: int = 1):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        torch.cuda.synchronize()
+        ts.append((time.perf_counter() - t0) * 1e3)
+    return float(np.median(ts))
+
+
+def spreading_e2e(d, k: int = 20):
+    """e2e of BASELINE config 2 through the reference-facing plugin call: recommendSpreadMethod(U, M, train_df, val_df,
+    "HybridS") with HOST DataFrames in and the reference's dict{uid: [k ids]} out (reference recommend.py:59-115).
+    Inside the timed region: interaction upload, degree / operand packing, G GEMM, HybridS scaling, F GEMM, filtered
+    top-k, id download, dict construction and the np.save side effect."""
+    install_cfg("HybridS", k=k, lam=0.3)
+    from model.SpreadMethod.recommend import recommendSpreadMethod
+
+    tr, va, _ = d.split()
+    train_df, val_df = frames_of(d, tr, va)
+    out = {}
+
+    def call():
+        out["rec"] = recommendSpreadMethod(d.n_users, d.n_items, train_df, val_df, "HybridS")
+    ms = wall_ms(call, reps=3)
+    assert len(out["rec"]) == d.n_users
+    return {"ms": round(ms, 3), "users_per_s": round(d.n_users / (ms * 1e-3), 1), "unit": "users/s",
+            "h2d_bytes_per_step": int(2 * 8 * (tr.size + va.size)), "d2h_bytes_per_step": int(d.n_users * k * 8),
+            "what": "recommendSpreadMethod(U, M, train_df, val_df, 'HybridS'): host DataFrames -> dict{uid: top-20}, wall "
+                    "clock incl. upload, packing, G, scale, F, top-k, download, dict + np.save (median of 3)"}
+
+
+def fusion_leg(dev):
+    """BASELINE config 3: SpreadLightGCNOpti on the Douban shape — (layer-0 score of the feature-initialised LightGCNOpti,
+    masked to -1024) * (A . HybridS(lambda)) -> filtered top-20, one B200."""
+    install_cfg("SpreadLightGCNOpti", dataset="douban", k=20, lam=0.3)
+    from lgcnhs_b200 import fusion
+    from model.LightGCNOpti.model import LightGCNOpti
+
+    d = load_shape("douban")
+    tr, va, _ = d.split()
+    train_df, val_df = frames_of(d, tr, va)
+    rng = np.random.default_rng(3)
+    torch.manual_seed(42)
+    model = LightGCNOpti(d.n_users, d.n_items, DIM, K_LAYERS, torch.from_numpy(rng.random((d.n_users, 29)).astype(np.float32)),
+                         torch.from_numpy(rng.random((d.n_items, 31)).astype(np.float32))).to(dev)
+    out = {}
+
+    def call():
+        out["idx"] = fusion.fused_recommend(model, d.n_users, d.n_items, train_df, val_df, 0.3, 20).cpu()
+    ms = wall_ms(call, reps=5)
+    flops = 2.0 * d.n_items * d.n_items * d.n_users * 2
+    return {"workload": f"SpreadLightGCNOpti fused recommend, douban shape ({d.n_users}x{d.n_items}, nnz(A)={tr.size + va.size})",
+            "ms": round(ms, 3), "users_per_s": round(d.n_users / (ms * 1e-3), 1),
+            "useful_tflops": round(flops / (ms * 1e-3) / 1e12, 2),
+            "what": "host DataFrames -> (U, 20) ids on the host: upload, G = A^T K_u^-1 A (16 000^2), HybridS scaling, "
+                    "F = A.W, fused layer-0 score x F top-20 (lgc_score_topk mul), download; wall clock, median of 5"}
+
+
 def spreading_leg(dev, steps: int, warmup: int):
     """BASELINE config 2: ML-1M shape, G once, then per lambda: scale + F = A.W + filtered top-20."""
     from lgcnhs_b200 import ops
@@ -270,7 +383,12 @@ def spreading_leg(dev, steps: int, warmup: int):
     t_f = ev[4].elapsed_time(ev[5]) / steps * 1e-3
     _, peak_burst, _, how = peaks()
     flops = 2.0 * M * M * U
+    try:
+        e2e = spreading_e2e(d)
+    except Exception as e:
+        e2e = {"error": repr(e)[:300]}
     return {
+        "e2e": e2e,
         "workload": f"hybrid spreading ml-1m shape ({U}x{M}, nnz(A)={sel.size}), top-20 full-rank filtered",
         "g_gemm": {"ms": round(t_g * 1e3, 4), "tflops": round(flops / t_g / 1e12, 2),
                    "kind": "G = A^T K_u^-1 A, u8 x4 digit planes of round(2^s/k_u), exact int32 accumulate",
@@ -423,14 +541,38 @@ def training_leg(dev, steps: int, warmup: int):
     e1.record()
     torch.cuda.synchronize()
     ms_eval = e0.elapsed_time(e1)
+    # e2e of the full-rank recommendation through the reference-facing call: recommendForAllUser(model, U, M, train_adj,
+    # val_adj, test_adj, k) with the HOST adjacency tensors buildGraph returns -> dict{uid: [k ids]} (+ np.save)
+    try:
+        install_cfg("LightGCN", k=20)
+        from model.LightGCN.recommend import recommendForAllUser
+
+        adj_host = torch.from_numpy(adj_np)
+        val_host = torch.from_numpy(bipartite(d, va))
+        test_host = torch.from_numpy(bipartite(d, te))
+        out = {}
+
+        def call():
+            out["rec"] = recommendForAllUser(model, d.n_users, d.n_items, adj_host, val_host, test_host, 20)
+        ms_e2e = wall_ms(call, reps=3)
+        eval_e2e = {"ms": round(ms_e2e, 2), "users_per_s": round(d.n_users / (ms_e2e * 1e-3), 1), "unit": "users/s",
+                    "h2d_bytes_per_step": int((adj_host.numel() + val_host.numel() + test_host.numel()) * 8),
+                    "d2h_bytes_per_step": int(d.n_users * 20 * 8),
+                    "what": "recommendForAllUser(model, U, M, train_adj, val_adj, test_adj, 20): host adjacency tensors -> "
+                            "dict{uid: top-20}; wall clock incl. upload, adjacency -> edge list, mask CSR, fused score/top-k "
+                            "kernel, download, dict + np.save (median of 3)"}
+    except Exception as e:
+        eval_e2e = {"error": repr(e)[:300]}
     hbm = peaks()[0]
     gbs = trainer.step_bytes(B) / (ms * 1e-3) / 1e9
+    gbs_c = trainer.step_bytes_compulsory(B) / (ms * 1e-3) / 1e9
     return {"workload": f"LightGCN K=3 D=64 BPR step (batch {B}) + full-rank top-20 eval, amazon-book shape "
                         f"(U={d.n_users}, M={d.n_items}, nnz={adj_np.shape[1]})",
             "step_ms": round(ms, 4), "loss": round(float(loss[0]), 5),
-            "step_algorithmic_gbs": round(gbs, 1), "step_frac_of_hbm_peak": round(gbs / hbm, 3),
+            "step_compulsory_gbs": round(gbs_c, 1), "step_frac_of_hbm_peak": round(gbs_c / hbm, 4),
+            "step_no_reuse_gbs": round(gbs, 1),
             "what": "device mini-batch + negative sampling kernel, then ONE CUDA graph per step: 2K fused SpMM layers (fwd + grad) + fused BPR fwd/bwd scatter + Adam (device-resident bias corrections); no host sync",
-            "eval_ms": round(ms_eval, 2), "eval_users_per_s": round(d.n_users / (ms_eval * 1e-3), 1),
+            "eval_ms": round(ms_eval, 2), "eval_users_per_s": round(d.n_users / (ms_eval * 1e-3), 1), "eval_e2e": eval_e2e,
             "eval_what": "ONE fused kernel: layer-0 score tiles (packed fp32 FMA) + train-pair fill(-1024) + top-20 over all 91 599 items; the U x M score matrix is never written; the mask CSR of the train pairs is built once per graph (2nd evaluation timed)"}
 
 
@@ -533,6 +675,18 @@ def main():
         ms = float(t.item())
     bytes_step = prop_bytes(nnz, n)
     value = bytes_step / (ms * 1e-3) / 1e9
+    parity_vs_1gpu = None
+    if world > 1:
+        # every rank recomputes the K-layer mean on ONE GPU and compares it with the replica the partitioned path left
+        # on it: the multi-GPU result must equal the single-GPU one to fp32 round-off (a row's summation path depends on
+        # the launch it is part of), on every rank
+        ref = ops.NormGraph(adj, n).propagate_mean(x0, K_LAYERS)
+        got = prop.propagate_mean(x0, K_LAYERS)
+        rel = ((got - ref).abs().max() / ref.abs().max()).reshape(1)
+        torch.distributed.all_reduce(rel, op=torch.distributed.ReduceOp.MAX)
+        parity_vs_1gpu = {"max_abs_diff_over_max_abs": float(rel.item()), "tolerance": 2e-6,
+                          "ok": bool(rel.item() <= 2e-6), "what": "K-layer mean on every rank vs the same call on one GPU"}
+        del ref, got
 
     line = None
     if rank == 0:
@@ -551,17 +705,37 @@ def main():
         }
         per_layer_ms = ms / K_LAYERS
         compulsory = nnz * 8 + (n + 1) * 4 + 2 * n * 4 * DIM
+        comp_gbs = compulsory / (per_layer_ms * 1e-3) / 1e9
+        gather_gbs = nnz * 4 * DIM / (per_layer_ms * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic(f"spmm_layer_kernel/{args.shape}")
         line["roofline"] = {
-            "bound": "hbm", "achieved": round(value, 2), "peak": hbm, "unit": "GB/s", "frac": round(value / hbm, 4),
-            "traffic": NCU_SPMM_DRAM_BYTES.get(args.shape), "kernel": "spmm_layer_kernel<64,0,UN>",
+            "bound": "hbm", "achieved": round(comp_gbs, 2), "peak": hbm, "unit": "GB/s",
+            "frac": round(comp_gbs / hbm / world, 4),
+            "traffic": traffic, "traffic_source": traffic_src, "kernel": "spmm_layer_kernel<64,NPEER,UN>",
             "us_per_layer": round(per_layer_ms * 1e3, 2),
-            "compulsory_frac": round(compulsory / (per_layer_ms * 1e-3) / 1e9 / hbm, 4),
-            "note": f"algorithmic bytes = no-reuse model 264 B/nnz + 260 B/node per layer; peak = {how} HBM copy "
-                    "bandwidth; X is L2-resident so the no-reuse fraction may exceed 1 (SURVEY.md 8d): the gathers are "
-                    "served by L2 at the rates in `ncu` (profiles/r1_ncu_all_kernels.txt), DRAM traffic = `traffic`",
-            "ncu": {"l1tex_throughput_pct": 71.4, "lts_throughput_pct": 60.4, "dram_throughput_pct": 8.4,
-                    "warps_active_pct": 96.6, "source": "profiles/r1_ncu_all_kernels.txt (same kernel, same graph)"},
+            "bytes_model": "COMPULSORY bytes per layer = nnz*8 (colidx + val, streamed once) + (N+1)*4 (rowptr) + 2*N*4*D "
+                           "(X read once, Y written once): every byte the layer must move through HBM, a true <= 1 bound "
+                           f"against the {how} HBM copy bandwidth (x n_gpus)",
+            "no_reuse_gbs": round(value, 2), "no_reuse_frac": round(value / hbm / world, 4),
+            "no_reuse_note": "`value` uses SURVEY.md 8d's no-reuse model (264 B/nnz + 260 B/node per layer: one 256-B row "
+                             "gather per non-zero).  X (42 MB) is L2-resident, so those gathers are served by L2 and "
+                             "no_reuse_frac is NOT an HBM fraction (it exceeds 1); the gathers have their own bound below",
         }
+        # L2 gather bound: the 256-B row gathers (nnz * 4D bytes per layer) against this GPU's measured throughput for
+        # uniformly random whole-row reads from a table of X's size (lgc_probe_gather, same LDG.128 x 16-lane pattern)
+        try:
+            pr = ops.probe_gather_gbs(n, DIM, n_gathers=nnz, device=dev)
+            line["roofline"]["l2_gather"] = {
+                "achieved": round(gather_gbs, 1), "peak": round(pr["gbs"], 1), "unit": "GB/s",
+                "frac": round(gather_gbs / pr["gbs"] / world, 4),
+                "bytes_model": "nnz * 4 * D gathered row bytes per layer / time",
+                "probe": {"what": "lgc_probe_gather: uniformly random whole-row reads (LDG.128 x 16 lanes) from an (N, 64) fp32 "
+                                  "table, 64 warps/SM, 8 gathers in flight per lane, measured in this run (best of 5)",
+                          "table_mb": round(pr["table_mb"], 1), "rows": pr["rows"], "us": round(pr["us"], 1)}}
+        except Exception as e:
+            line["roofline"]["l2_gather"] = {"error": repr(e)[:200]}
+        if world > 1:
+            line["parity_vs_1gpu"] = parity_vs_1gpu
 
     # ---- e2e through the reference-facing module call, host buffers, N GPUs ----
     from model.LightGCN.model import LightGCN
@@ -641,6 +815,10 @@ def main():
             line["training"] = training_leg(dev, steps=max(5, min(args.steps, 20)), warmup=3)
         except Exception as e:
             line["training"] = {"error": repr(e)[:300]}
+        try:
+            line["fusion"] = fusion_leg(dev)
+        except Exception as e:
+            line["fusion"] = {"error": repr(e)[:300]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         gbs, sec = cpu_prop_sample(adj_np, d.n_users, d.n_items, steps=1, warmup=1)
         line["cpu_baseline"] = {"value": round(gbs, 3), "unit": "GB/s", "cores": torch.get_num_threads(), "kind": "port",

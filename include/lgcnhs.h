@@ -352,6 +352,18 @@ int lgc_spmm_layer_bcast(const int32_t* rowptr, const int32_t* colidx, const flo
                          float* const* peer_Y_host, int32_t n_peers, float* partial,
                          int32_t* counters, lgc_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * Measurement probe (bench.py): uniformly random whole-row reads (dim fp32 per row, 128-bit
+ * per lane) from an (n_rows, dim) table at full occupancy — the gather pattern of the
+ * propagation SpMM with everything else removed.  Its bytes / time is the L2 gather peak the
+ * SpMM's gather fraction is stated against.  out: lgc_probe_gather_threads() floats of
+ * scratch; *gathers_done_host receives the number of rows actually read (>= n_gathers).
+ * No reference counterpart (the reference has no benchmark harness).
+ * ---------------------------------------------------------------------------------- */
+int64_t lgc_probe_gather_threads(void);
+int lgc_probe_gather(const float* table, int64_t n_rows, int32_t dim, int64_t n_gathers,
+                     uint32_t seed, float* out, int64_t* gathers_done_host, lgc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -218,6 +218,28 @@ class NormGraph:
         return self.nnz * 8 + (self.n_nodes + 1) * 4 + 2 * self.n_nodes * 4 * dim
 
 
+def probe_gather_gbs(n_rows: int, dim: int = 64, n_gathers: int = 32_000_000, reps: int = 5, device=None) -> dict:
+    """Measured throughput of random whole-row gathers from an (n_rows, dim) fp32 table (lgc_probe_gather): the L2
+    gather peak of this GPU for this table size.  Returns {"gbs", "us", "rows", "table_mb"}; best of `reps`."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    table = torch.randn((n_rows, dim), dtype=torch.float32, device=dev)
+    out = torch.empty(int(lib().lgc_probe_gather_threads()), dtype=torch.float32, device=dev)
+    done = C.c_int64(0)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    best = float("inf")
+    for r in range(reps + 1):
+        ev[0].record()
+        check(lib().lgc_probe_gather(_ptr(table), n_rows, dim, n_gathers, 1234 + r, _ptr(out), C.byref(done), _stream()),
+              "probe gather")
+        ev[1].record()
+        torch.cuda.synchronize()
+        if r > 0:
+            best = min(best, ev[0].elapsed_time(ev[1]))
+    nbytes = done.value * dim * 4
+    return {"gbs": nbytes / (best * 1e-3) / 1e9, "us": best * 1e3, "rows": int(done.value),
+            "table_mb": n_rows * dim * 4 / 1e6}
+
+
 # --------------------------------------------------------------------------------------------
 # (P4/P6/P7) BPR + Adam
 # --------------------------------------------------------------------------------------------

@@ -115,6 +115,10 @@ class FusedBPRTrainer:
     def step_bytes(self, batch: int) -> int:
         return 2 * self.K * self.g.layer_bytes(self.D) + batch * 12 * 4 * self.D + 7 * self.N * 4 * self.D
 
+    # compulsory bytes of one step: every operand moved once (the row gathers of the SpMM are L2-served re-reads)
+    def step_bytes_compulsory(self, batch: int) -> int:
+        return 2 * self.K * self.g.layer_bytes_compulsory(self.D) + batch * 12 * 4 * self.D + 7 * self.N * 4 * self.D
+
 
 def choose_device() -> torch.device:
     """The reference hard-codes 'cuda:1' (train.py:87); use the current CUDA device and refuse the CPU."""

@@ -37,8 +37,9 @@ def _save(all_user_recommend_dict: dict) -> None:
 def recommendForAllUser(model: LightGCN, user_num: int, item_num: int, train_edge_index: torch.Tensor,
                         val_edge_index: torch.Tensor, test_edge_index: torch.Tensor, k: int) -> dict:
     """top-k of e_u^0 . e_i^0^T with train AND val pairs masked to -1024 (reference recommend.py:68-125)."""
-    train_ei = convertAdjMatrixToEdgeIndex(user_num, item_num, train_edge_index)
-    val_ei = convertAdjMatrixToEdgeIndex(user_num, item_num, val_edge_index)
+    dev = model.users_emb.weight.device          # buildGraph hands over host tensors: convert on the device
+    train_ei = convertAdjMatrixToEdgeIndex(user_num, item_num, train_edge_index.to(dev))
+    val_ei = convertAdjMatrixToEdgeIndex(user_num, item_num, val_edge_index.to(dev))
     rec = _topk_layer0(model, user_num, item_num, [train_ei, val_ei], k).cpu().tolist()
     all_user_recommend_dict = {uid: items for uid, items in enumerate(rec)}
     _save(all_user_recommend_dict)
