@@ -27,6 +27,7 @@
 //   warps 2..5  epilogue      : tcgen05.ld 32x32b -> combine planes -> scale -> fp32 store,
 //                               overlapped with the next tile's main loop
 #include "umma_common.cuh"
+#include "select.cuh"
 
 namespace lgc {
 namespace umma {
@@ -43,7 +44,77 @@ struct GemmParams {
   double scale;
   int k_elems_per_kb;  // 64 (bf16) or 128 (u8)
   int chunk_kb;        // K-blocks accumulated in TMEM before a drain (>= num_kb: single chunk)
+  // ---- tile schedule of the CTA-pair kernel ----
+  //   0: every tile, column-block major (consecutive clusters share a B tile through L2)
+  //   1: SYMMETRIC output (C == C^T bit for bit, M == N): only tiles that touch the upper triangle are computed,
+  //      tiles strictly above the diagonal blocks also store their transpose
+  //   2: ROW-OWNER segments (fused top-k): a work item is (256-row block, one of `segs` ranges of column tiles);
+  //      the epilogue threads keep their row's selection state in registers across the item's tiles
+  int mode;
+  int segs;
+  // ---- fused row-wise top-k epilogue (mode 2) ----
+  const uint32_t* excl;          // bit-packed exclusion matrix (row r, col c -> bit (excl_row0 + r)*excl_stride + c) or null
+  long long excl_stride, excl_row0;
+  int k;
+  unsigned long long* cand;      // [M * segs][kCandCap] candidate keys
+  int* cand_cnt;                 // [M * segs]
 };
+
+constexpr int kCandCap = 128;    // per (row, segment) candidate buffer of the fused top-k epilogue (k <= 32)
+
+struct TileSched {
+  int m, n, seg, n_end;
+  bool first, last, started;
+  long long w;
+};
+
+// number of 256-row blocks of column tile n that touch the upper triangle (symmetric schedule)
+__device__ __forceinline__ int sym_rows(const GemmParams& p, int n) {
+  const long long c = ((long long)(n + 1) * p.NB - 1) / 256 + 1;
+  return c < p.tiles_m ? (int)c : p.tiles_m;
+}
+
+// Every role of the CTA pair (both producers, the MMA issuer, all epilogue warps) walks the SAME sequence of tiles.
+__device__ __forceinline__ bool sched_next(TileSched& s, const GemmParams& p, int cluster_id, int n_clusters) {
+  if (p.mode == 0) {
+    s.w = s.started ? s.w + n_clusters : cluster_id;
+    s.started = true;
+    if (s.w >= (long long)p.tiles_m * p.tiles_n) return false;
+    s.m = (int)(s.w % p.tiles_m);
+    s.n = (int)(s.w / p.tiles_m);
+    return true;
+  }
+  if (p.mode == 1) {
+    if (!s.started) { s.started = true; s.m = cluster_id; s.n = 0; }
+    else s.m += n_clusters;
+    while (s.n < p.tiles_n) {
+      const int c = sym_rows(p, s.n);
+      if (s.m < c) return true;
+      s.m -= c;
+      ++s.n;
+    }
+    return false;
+  }
+  if (s.started && s.n + 1 < s.n_end) {
+    ++s.n;
+    s.first = false;
+    s.last = (s.n + 1 == s.n_end);
+    return true;
+  }
+  s.w = s.started ? s.w + n_clusters : cluster_id;
+  s.started = true;
+  while (s.w < (long long)p.tiles_m * p.segs) {
+    s.m = (int)(s.w / p.segs);
+    s.seg = (int)(s.w % p.segs);
+    const int n0 = (int)((long long)s.seg * p.tiles_n / p.segs), n1 = (int)((long long)(s.seg + 1) * p.tiles_n / p.segs);
+    if (n1 > n0) {
+      s.n = n0; s.n_end = n1; s.first = true; s.last = (n0 + 1 == n1);
+      return true;
+    }
+    s.w += n_clusters;
+  }
+  return false;
+}
 
 template <int KIND, int PLANES>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -293,7 +364,8 @@ constexpr int kPBStage = 128 * kKBytes;  // 16 KB
 constexpr int kPStageBytes = kAStage + kPBStage;
 static_assert((size_t)kPStages * kPStageBytes <= (size_t)kStages * kStageBytes, "pair pipeline must fit the same smem budget");
 
-template <int KIND, int PLANES>
+// EPI 0: store C (optionally mirrored, schedule 1);  EPI 1: fused row-wise top-k (schedule 2), C is never written.
+template <int KIND, int PLANES, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                       const __grid_constant__ CUtensorMap tmapBh, const GemmParams p) {
@@ -315,7 +387,6 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
   constexpr int NB = PLANES == 3 ? 80 : PLANES == 4 ? 64 : 128;  // output columns per tile
   constexpr int n_mma = PLANES * NB;                              // MMA N (both halves)
   constexpr int H = n_mma / 2;                                    // B rows staged by each CTA
-  const int num_tiles = p.tiles_m * p.tiles_n;                    // tiles_m counts 256-row tiles here
   const int n_chunks = (p.num_kb + p.chunk_kb - 1) / p.chunk_kb;
 
   if (threadIdx.x == 0) {
@@ -344,8 +415,9 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
       const uint32_t cta_tx = (uint32_t)(kAStage + H * kKBytes);
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = cluster_id; t < num_tiles; t += n_clusters) {
-        const int m_blk = t % p.tiles_m, n_blk = t / p.tiles_m;
+      TileSched ts{};
+      while (sched_next(ts, p, cluster_id, n_clusters)) {
+        const int m_blk = ts.m, n_blk = ts.n;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           if (leader) mbar_expect_tx(&full[stage], 2 * cta_tx);
@@ -383,7 +455,8 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int t = cluster_id; t < num_tiles; t += n_clusters) {
+      TileSched ts{};
+      while (sched_next(ts, p, cluster_id, n_clusters)) {
         for (int ch = 0; ch < n_chunks; ++ch, ++it) {
           const int acc = it & 1;
           const uint32_t acc_phase = (it >> 1) & 1;
@@ -414,12 +487,24 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
     // ------------------------------ epilogue (warps 2..5, both CTAs) ------------------------------
     const int q = warp & 3;
     int it = 0;
-    for (int t = cluster_id; t < num_tiles; t += n_clusters) {
-      const int m_blk = t % p.tiles_m, n_blk = t / p.tiles_m;
+    // fused top-k state of this thread's row (EPI 1): threshold key / value and fill of its candidate buffer
+    unsigned long long sel_thr = 0ull;
+    float sel_thr_f = -INFINITY;
+    int sel_cnt = 0;
+    unsigned long long* sel_buf = nullptr;
+    TileSched ts{};
+    while (sched_next(ts, p, cluster_id, n_clusters)) {
+      const int m_blk = ts.m, n_blk = ts.n;
       const int64_t row = (int64_t)m_blk * 256 + (int64_t)rank * kBlockM + q * 32 + lane;
       const bool row_ok = row < p.M;
       const float rscale = (row_ok && p.rs) ? __ldg(p.rs + row) : 1.0f;
-      float* crow = p.C + (row_ok ? row : 0) * p.ldc;
+      float* crow = (EPI == 0) ? p.C + (row_ok ? row : 0) * p.ldc : nullptr;
+      // schedule 1: this tile lies strictly above the diagonal blocks -> its transpose is not computed anywhere else
+      const bool mirror = EPI == 0 && p.mode == 1 && (long long)n_blk * NB >= (long long)(m_blk + 1) * 256;
+      if (EPI == 1 && ts.first) {
+        sel_thr = 0ull; sel_thr_f = -INFINITY; sel_cnt = 0;
+        sel_buf = p.cand + ((size_t)(row_ok ? row : 0) * p.segs + ts.seg) * kCandCap;
+      }
       float run[NB];
       for (int ch = 0; ch < n_chunks; ++ch, ++it) {
         const int acc = it & 1;
@@ -459,22 +544,73 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
               const float cscale = (p.cs && col < p.N) ? __ldg(p.cs + col) : 1.0f;
               out[j] = out[j] * rscale * cscale;
             }
-            if (row_ok) {
-              if (col0 + 16 <= p.N && (p.ldc & 3) == 0 && ((uintptr_t)p.C & 15) == 0) {
+            if (EPI == 0) {
+              if (row_ok) {
+                if (col0 + 16 <= p.N && (p.ldc & 3) == 0 && ((uintptr_t)p.C & 15) == 0) {
 #pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                  *reinterpret_cast<float4*>(crow + col0 + j) = make_float4(out[j], out[j + 1], out[j + 2], out[j + 3]);
-              } else {
+                  for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(crow + col0 + j) = make_float4(out[j], out[j + 1], out[j + 2], out[j + 3]);
+                } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                  if (col0 + j < p.N) crow[col0 + j] = out[j];
+                  for (int j = 0; j < 16; ++j)
+                    if (col0 + j < p.N) crow[col0 + j] = out[j];
+                }
+                if (mirror) {
+                  // C[col, row] = C[row, col]: for a fixed j the 32 lanes of the warp own 32 consecutive rows, so
+                  // each of these stores is one coalesced 128-byte segment of row (col0 + j) of C
+#pragma unroll
+                  for (int j = 0; j < 16; ++j)
+                    if (col0 + j < p.N) p.C[(col0 + j) * p.ldc + row] = out[j];
+                }
+              }
+            } else {
+              // ---- fused selection: one float compare per value against the row's current k-th best; survivors get
+              //      their exact 64-bit key (value, column), pass the exclusion bit test and are appended to the
+              //      row's private buffer (plain stores: no other thread owns this row) ----
+              if (row_ok) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const int64_t col = col0 + j;
+                  if (out[j] >= sel_thr_f && col < p.N) {
+                    const unsigned long long key = make_key(float_key(out[j]), (uint32_t)col);
+                    if (key > sel_thr) {
+                      bool ex = false;
+                      if (p.excl) {
+                        const long long b = (p.excl_row0 + row) * p.excl_stride + col;
+                        ex = (__ldg(p.excl + (b >> 5)) >> (b & 31)) & 1u;
+                      }
+                      if (!ex) sel_buf[sel_cnt++] = key;
+                    }
+                  }
+                }
               }
             }
           }
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_leader(&tempty[acc]);
+        if (lane == 0) mbar_arrive_leader(&tempty[acc]);   // the accumulator is free: the next tile's MMAs may start
+      }
+      if (EPI == 1) {
+        // rows whose buffer could overflow during the next tile are compacted now, one row at a time, by the whole
+        // warp (radix select in registers, select.cuh); the TMEM buffer has been released already, so this overlaps
+        // the tensor-core work of the following tiles
+        uint32_t need = __ballot_sync(0xffffffffu, sel_cnt + NB > kCandCap);
+        while (need) {
+          const int rl = __ffs(need) - 1;
+          need &= need - 1u;
+          unsigned long long* b = reinterpret_cast<unsigned long long*>(
+              __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(sel_buf), rl));
+          const int c = __shfl_sync(0xffffffffu, sel_cnt, rl);
+          unsigned long long t;
+          const int kept = warp_select<kCandCap / 32>(b, c, p.k, lane, &t);
+          if (lane == rl) {
+            sel_cnt = kept;
+            sel_thr = t;
+            sel_thr_f = t ? key_float((uint32_t)(t >> 32)) : -INFINITY;
+          }
+        }
+        if (ts.last && row_ok) p.cand_cnt[(size_t)row * p.segs + ts.seg] = sel_cnt;
       }
     }
   }
@@ -486,6 +622,37 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols)
                  : "memory");
+  }
+}
+
+// Final step of the fused top-k: one warp per row merges the candidate lists its `segs` segments left behind
+// (<= kCandCap keys each) and writes the k best, sorted (value descending, ties -> larger column first).
+constexpr int kMergeWarps = 8;
+__global__ void __launch_bounds__(kMergeWarps * 32)
+resource_topk_merge_kernel(const unsigned long long* __restrict__ cand, const int* __restrict__ cand_cnt, int64_t n_rows,
+                           int segs, int k, int64_t* __restrict__ out_idx, float* __restrict__ out_val) {
+  constexpr int CAPM = 2 * kCandCap;
+  __shared__ unsigned long long s_buf[kMergeWarps][CAPM];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t row = (int64_t)blockIdx.x * kMergeWarps + w;
+  if (row >= n_rows) return;
+  unsigned long long* buf = s_buf[w];
+  unsigned long long thr;
+  int cur = 0;
+  for (int sg = 0; sg < segs; ++sg) {
+    int c = cand_cnt[(size_t)row * segs + sg];
+    c = c < kCandCap ? c : kCandCap;
+    if (cur + c > CAPM) cur = warp_select<CAPM / 32>(buf, cur, k, lane, &thr);
+    const unsigned long long* src = cand + ((size_t)row * segs + sg) * kCandCap;
+    for (int i = lane; i < c; i += 32) buf[cur + i] = src[i];
+    cur += c;
+    __syncwarp();
+  }
+  const int kept = warp_compact<CAPM / 32>(buf, cur, k, lane, &thr);
+  for (int i = lane; i < k; i += 32) {
+    const unsigned long long key = buf[i];
+    out_idx[row * k + i] = i < kept ? (int64_t)(uint32_t)(key & 0xffffffffull) : -1;
+    if (out_val) out_val[row * k + i] = i < kept ? key_float((uint32_t)(key >> 32)) : -INFINITY;
   }
 }
 
@@ -558,12 +725,40 @@ static int check_gemm_args(int kind, const void* A, int64_t lda, const void* B, 
 using namespace lgc;
 using namespace lgc::umma;
 
-extern "C" int hs_gemm_planes(int32_t kind, const void* A, int64_t lda, const void* B, int64_t ldb,
-                              int64_t plane_stride, int32_t planes, int64_t M, int64_t N, int64_t K,
-                              float* C, int64_t ldc, const float* rs, const float* cs, double scale,
-                              lgc_stream_t stream_) {
-  int rc = check_gemm_args(kind, A, lda, B, ldb, plane_stride, planes, M, N, K, C, ldc);
-  if (rc) return rc;
+namespace lgc {
+namespace umma {
+
+struct TopkArgs {
+  const uint32_t* excl;
+  int64_t excl_stride, excl_row0;
+  int k;
+  int64_t* out_idx;
+  float* out_val;
+  void* scratch;
+  size_t scratch_bytes;
+};
+
+// segments per 256-row block of the fused top-k schedule: fill the machine when there are fewer row blocks than
+// CTA pairs (ML-1M: 24 row blocks x 3 segments = 72 work items on 74 pairs), one segment otherwise
+static int topk_segments(int64_t M, int64_t N, int planes) {
+  const int NB = planes == 3 ? 80 : planes == 4 ? 64 : 128;
+  const int64_t tiles_m = ceil_div(M, 256), tiles_n = ceil_div(N, NB);
+  const int clusters = num_sms() / 2;
+  int64_t segs = tiles_m >= clusters ? 1 : clusters / tiles_m;
+  if (segs > tiles_n) segs = tiles_n;
+  return (int)(segs < 1 ? 1 : segs);
+}
+
+static size_t topk_scratch_bytes(int64_t M, int64_t N, int planes) {
+  const size_t rows = (size_t)M * topk_segments(M, N, planes);
+  return align_up(rows * kCandCap * sizeof(unsigned long long), 256) + align_up(rows * sizeof(int), 256);
+}
+
+// mode 0: plain; 1: symmetric output (kind 1, M == N, no row/column scales); 2: fused top-k (topk != null)
+static int gemm_planes_impl(int32_t kind, const void* A, int64_t lda, const void* B, int64_t ldb,
+                            int64_t plane_stride, int32_t planes, int64_t M, int64_t N, int64_t K, float* C, int64_t ldc,
+                            const float* rs, const float* cs, double scale, int mode, const TopkArgs* topk,
+                            lgc_stream_t stream_) {
   const int esize = kind == 0 ? 2 : 1;
   LGC_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "gemm: operands must be 16-byte aligned");
   LGC_REQUIRE((lda * esize) % 16 == 0 && (ldb * esize) % 16 == 0 && (plane_stride * esize) % 16 == 0,
@@ -607,9 +802,12 @@ extern "C" int hs_gemm_planes(int32_t kind, const void* A, int64_t lda, const vo
   p.C = C; p.ldc = ldc; p.rs = rs; p.cs = cs; p.scale = scale;
   p.k_elems_per_kb = k_elems;
   p.chunk_kb = kind == 0 ? g_chunk_kb : p.num_kb;  // int32 accumulation is exact: one chunk
+  p.mode = 0; p.segs = 1;
   cudaStream_t stream = (cudaStream_t)stream_;
 
-  if (g_use_pair && M > kBlockM) {
+  const bool pair = (g_use_pair || mode == 2) && M > kBlockM;
+  if (mode == 2 && !pair) LGC_FAIL(LGC_ERR_UNSUPPORTED, "resource_topk: needs more than 128 rows (CTA-pair kernel)");
+  if (pair) {
     // CTA-pair kernel: 256-row tiles, each CTA stages half of the stacked plane rows of B
     CUtensorMap tmBh;
     {
@@ -623,24 +821,51 @@ extern "C" int hs_gemm_planes(int32_t kind, const void* A, int64_t lda, const vo
       if (r != CUDA_SUCCESS) LGC_FAIL(LGC_ERR_CUDA, "gemm: cuTensorMapEncodeTiled(B half) failed with %d", (int)r);
     }
     p.tiles_m = (int)ceil_div(M, 256);
-    const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
+    p.mode = mode;
+    int64_t work = (int64_t)p.tiles_m * p.tiles_n;
+    if (mode == 1) {
+      work = 0;
+      for (int n = 0; n < p.tiles_n; ++n) {
+        const int64_t c = ((int64_t)(n + 1) * NB - 1) / 256 + 1;
+        work += c < p.tiles_m ? c : p.tiles_m;
+      }
+    } else if (mode == 2) {
+      p.segs = topk_segments(M, N, planes);
+      work = (int64_t)p.tiles_m * p.segs;
+      const size_t rows = (size_t)M * p.segs;
+      LGC_REQUIRE(topk->scratch && topk->scratch_bytes >= topk_scratch_bytes(M, N, planes), "resource_topk: scratch too small");
+      LGC_REQUIRE(((uintptr_t)topk->scratch & 255) == 0, "resource_topk: scratch must be 256-byte aligned");
+      p.cand = reinterpret_cast<unsigned long long*>(topk->scratch);
+      p.cand_cnt = reinterpret_cast<int*>(reinterpret_cast<char*>(topk->scratch) +
+                                          align_up(rows * kCandCap * sizeof(unsigned long long), 256));
+      p.excl = topk->excl; p.excl_stride = topk->excl_stride; p.excl_row0 = topk->excl_row0; p.k = topk->k;
+    }
     int clusters = num_sms() / 2;
-    if (tiles < clusters) clusters = (int)tiles;
+    if (work < clusters) clusters = (int)work;
     const int grid = 2 * clusters;
-#define LGC_GEMM_PAIR_CASE(KD, PL)                                                                              \
-  if (kind == KD && planes == PL) {                                                                             \
-    static DeviceOnce attr;                                                                                        \
-    if (attr.need()) {                                                                                                \
-      LGC_CUDA(cudaFuncSetAttribute(umma_gemm_pair_kernel<KD, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                    (int)kSmemBytes));                                                          \
-      attr.mark();                                                                                               \
+    bool launched = false;
+#define LGC_GEMM_PAIR_CASE(KD, PL, EP)                                                                          \
+  if (kind == KD && planes == PL && (mode == 2) == (EP == 1)) {                                                 \
+    static DeviceOnce attr;                                                                                     \
+    if (attr.need()) {                                                                                          \
+      LGC_CUDA(cudaFuncSetAttribute(umma_gemm_pair_kernel<KD, PL, EP>,                                          \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));             \
+      attr.mark();                                                                                              \
     }                                                                                                           \
-    umma_gemm_pair_kernel<KD, PL><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmBh, p);                   \
+    umma_gemm_pair_kernel<KD, PL, EP><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmBh, p);               \
+    launched = true;                                                                                            \
   }
-    LGC_GEMM_PAIR_CASE(0, 1) LGC_GEMM_PAIR_CASE(0, 2) LGC_GEMM_PAIR_CASE(0, 3)
-    LGC_GEMM_PAIR_CASE(1, 1) LGC_GEMM_PAIR_CASE(1, 2) LGC_GEMM_PAIR_CASE(1, 3) LGC_GEMM_PAIR_CASE(1, 4)
+    LGC_GEMM_PAIR_CASE(0, 1, 0) LGC_GEMM_PAIR_CASE(0, 2, 0) LGC_GEMM_PAIR_CASE(0, 3, 0)
+    LGC_GEMM_PAIR_CASE(1, 1, 0) LGC_GEMM_PAIR_CASE(1, 2, 0) LGC_GEMM_PAIR_CASE(1, 3, 0) LGC_GEMM_PAIR_CASE(1, 4, 0)
+    LGC_GEMM_PAIR_CASE(1, 3, 1) LGC_GEMM_PAIR_CASE(1, 4, 1)
 #undef LGC_GEMM_PAIR_CASE
+    if (!launched) LGC_FAIL(LGC_ERR_UNSUPPORTED, "gemm: kind %d / %d planes not available in this mode", kind, planes);
     LGC_LAUNCH_CHECK("umma_gemm_pair_kernel");
+    if (mode == 2) {
+      resource_topk_merge_kernel<<<(unsigned)ceil_div(M, kMergeWarps), kMergeWarps * 32, 0, stream>>>(
+          p.cand, p.cand_cnt, M, p.segs, topk->k, topk->out_idx, topk->out_val);
+      LGC_LAUNCH_CHECK("resource_topk_merge_kernel");
+    }
     return LGC_OK;
   }
 
@@ -648,11 +873,11 @@ extern "C" int hs_gemm_planes(int32_t kind, const void* A, int64_t lda, const vo
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
 #define LGC_GEMM_CASE(KD, PL)                                                                             \
   if (kind == KD && planes == PL) {                                                                       \
-    static DeviceOnce attr;                                                                                  \
-    if (attr.need()) {                                                                                          \
+    static DeviceOnce attr;                                                                               \
+    if (attr.need()) {                                                                                    \
       LGC_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<KD, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                     (int)kSmemBytes));                                                    \
-      attr.mark();                                                                                         \
+      attr.mark();                                                                                        \
     }                                                                                                     \
     umma_gemm_kernel<KD, PL><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, p);                        \
   }
@@ -661,6 +886,48 @@ extern "C" int hs_gemm_planes(int32_t kind, const void* A, int64_t lda, const vo
 #undef LGC_GEMM_CASE
   LGC_LAUNCH_CHECK("umma_gemm_kernel");
   return LGC_OK;
+}
+
+}  // namespace umma
+}  // namespace lgc
+
+extern "C" int hs_gemm_planes(int32_t kind, const void* A, int64_t lda, const void* B, int64_t ldb,
+                              int64_t plane_stride, int32_t planes, int64_t M, int64_t N, int64_t K,
+                              float* C, int64_t ldc, const float* rs, const float* cs, double scale,
+                              lgc_stream_t stream_) {
+  int rc = check_gemm_args(kind, A, lda, B, ldb, plane_stride, planes, M, N, K, C, ldc);
+  if (rc) return rc;
+  return gemm_planes_impl(kind, A, lda, B, ldb, plane_stride, planes, M, N, K, C, ldc, rs, cs, scale, 0, nullptr, stream_);
+}
+
+extern "C" int hs_gemm_planes_sym(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t plane_stride,
+                                  int32_t planes, int64_t N, int64_t K, float* C, int64_t ldc, double scale,
+                                  lgc_stream_t stream_) {
+  int rc = check_gemm_args(1, A, lda, B, ldb, plane_stride, planes, N, N, K, C, ldc);
+  if (rc) return rc;
+  return gemm_planes_impl(1, A, lda, B, ldb, plane_stride, planes, N, N, K, C, ldc, nullptr, nullptr, scale, 1, nullptr,
+                          stream_);
+}
+
+extern "C" int64_t hs_resource_topk_scratch_bytes(int64_t M, int64_t N, int32_t planes) {
+  if (M <= 0 || N <= 0) return 0;
+  return (int64_t)topk_scratch_bytes(M, N, planes);
+}
+
+extern "C" int hs_resource_topk(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t plane_stride,
+                                int32_t planes, int64_t M, int64_t N, int64_t K, const float* cs, double scale,
+                                const uint32_t* excl_mask, int64_t mask_stride_bits, int64_t row_offset, int32_t k,
+                                int64_t* out_idx, float* out_val, void* scratch, int64_t scratch_bytes,
+                                lgc_stream_t stream_) {
+  LGC_REQUIRE(A && B && out_idx && scratch, "resource_topk: null pointer");
+  LGC_REQUIRE(M > 0 && N > 0 && K > 0 && lda >= K && ldb >= K, "resource_topk: bad extents");
+  LGC_REQUIRE(planes == 3 || planes == 4, "resource_topk: 3 or 4 uint8 digit planes");
+  LGC_REQUIRE(plane_stride >= N * ldb, "resource_topk: plane stride overlaps planes");
+  LGC_REQUIRE(k >= 1 && k <= 32 && k <= N, "resource_topk: k must be in [1, min(32, N)]");
+  LGC_REQUIRE(!excl_mask || mask_stride_bits >= N, "resource_topk: mask stride smaller than the row");
+  LGC_REQUIRE(((uintptr_t)excl_mask & 3) == 0, "resource_topk: mask must be 4-byte aligned");
+  TopkArgs t{excl_mask, mask_stride_bits, row_offset, k, out_idx, out_val, scratch, (size_t)scratch_bytes};
+  return gemm_planes_impl(1, A, lda, B, ldb, plane_stride, planes, M, N, K, nullptr, N, nullptr, cs, scale, 2, &t, stream_);
 }
 
 extern "C" int hs_gemm_use_cta_pair(int32_t on) {

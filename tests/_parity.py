@@ -28,9 +28,11 @@ def assert_topk_parity(got_idx, ref_idx, ref_scores, what="", seen_mask=None, mi
     assert got.shape == ref.shape, f"{what}: list shape {got.shape} vs {ref.shape}"
     U, k = ref.shape
     assert got.min() >= 0 and got.max() < S.shape[1], f"{what}: id out of range"
-    scale = float(np.abs(S[np.isfinite(S)]).max())
     fv = np.take_along_axis(S, ref, axis=1).astype(np.float64)
     gv = np.take_along_axis(S, got, axis=1).astype(np.float64)
+    # absolute part of the tolerance: relative to the largest RANKED score, not to max|S| — the score matrices of the
+    # LightGCN family hold the -1024 fill (and -1024 * F in the fusion), which would inflate it 1000-fold
+    scale = float(np.abs(fv[np.isfinite(fv)]).max())
     tol = tol_mult * tol_of(fv, scale)
     bad = np.abs(gv - fv) > tol
     assert not bad.any(), f"{what}: score at rank differs at {int(bad.sum())} positions, max {np.abs(gv - fv).max():.3e}"

@@ -101,5 +101,5 @@ def test_main_sequence_fusion_family(dev, name):
     F_new = SO.fused_resource(Gs, SO.get_resource(A, SO.hybrids(A, SO.get_spreading_general_mat(A), 0.3)))
     ref_idx, _ = SO.recommend_fast(F_new, A, k)
     assert_topk_parity(res["recommendations"].numpy(), ref_idx, F_new, f"{name} main sequence", seen_mask=A > 0,
-                       min_checked=0.3, tol_mult=4.0)
+                       min_checked=0.1, tol_mult=4.0)
     _check_metrics(res, k)
