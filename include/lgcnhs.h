@@ -288,6 +288,35 @@ int hs_gemm_planes(int32_t kind, const void* A, int64_t lda, const void* B, int6
                    int64_t plane_stride, int32_t planes, int64_t M, int64_t N, int64_t K,
                    float* C, int64_t ldc, const float* rs, const float* cs, double scale,
                    lgc_stream_t stream);
+/* Same contraction for a SYMMETRIC result (kind 1 only: exact integer accumulation makes
+ * C == C^T bit for bit), as G = A^T K_u^-1 A is (model/SpreadMethod/model.py:25 with A := A^T,
+ * B_p := digit planes of round(2^s/k_u) A^T).  Only the tiles that touch the upper triangle
+ * are computed (about half the MMAs); tiles above the diagonal blocks also store their
+ * transpose.  C: (N x N) fp32.  Bit-identical to hs_gemm_planes. */
+int hs_gemm_planes_sym(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t plane_stride,
+                       int32_t planes, int64_t N, int64_t K, float* C, int64_t ldc, double scale,
+                       lgc_stream_t stream);
+/* ------------------------------------------------------------------------------------
+ * (S3+S4 fused) F = A . W and the per-user filtered top-k in ONE pass: the F tiles never
+ * leave TMEM/registers.  Replaces np.dot(A, W) (model/SpreadMethod/model.py:98) followed by
+ * the per-user np.argsort + Python `not in` filter loop (model/SpreadMethod/recommend.py:35-47).
+ *   value(u, j) = cs[j] * scale * sum_p 256^p sum_i A[u,i] * B_p[j,i]      (kind 1, exact int32)
+ *   excl_mask  : bit-packed (rows x N) matrix of pairs that must not be returned, bit
+ *                (row_offset + u) * mask_stride_bits + j; may be null (unfiltered ranking)
+ *   out_idx int64 (M, k), out_val fp32 (M, k) or null: sorted by value descending, ties ->
+ *                larger column first (what np.argsort(row)[::-1] gives); (-1, -inf) padding.
+ * Work item = (256-row block, segment of the column tiles); each epilogue thread keeps the
+ * threshold / fill count of its row in registers across the item's tiles and appends the
+ * few survivors to a private candidate buffer in `scratch`; a final warp-per-row kernel
+ * merges the segments.  planes in {3,4}, k <= 32, M > 128.  Lists are identical to
+ * hs_gemm_planes + lgc_topk_rows.  scratch: hs_resource_topk_scratch_bytes(), 256-B aligned.
+ * ---------------------------------------------------------------------------------- */
+int64_t hs_resource_topk_scratch_bytes(int64_t M, int64_t N, int32_t planes);
+int hs_resource_topk(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t plane_stride,
+                     int32_t planes, int64_t M, int64_t N, int64_t K, const float* cs, double scale,
+                     const uint32_t* excl_mask, int64_t mask_stride_bits, int64_t row_offset,
+                     int32_t k, int64_t* out_idx, float* out_val, void* scratch,
+                     int64_t scratch_bytes, lgc_stream_t stream);
 /* tcgen05 kind::f16 accumulates with truncation (measured: tools/probe_umma_numerics.py), so
  * the bf16 kind drains its TMEM accumulator into round-to-nearest fp32 registers every
  * chunk_kb K-blocks of 64 elements (default 8): error <= 4*chunk_kb*2^-23 per output,

@@ -494,6 +494,7 @@ class SpreadingEngine:
         self.G: Optional[torch.Tensor] = None
         self.C: Optional[torch.Tensor] = None
         self.Wt: Optional[torch.Tensor] = None
+        self._topk_scratch: Optional[torch.Tensor] = None
 
     def excl_items(self, u: int) -> torch.Tensor:
         """Deduplicated item ids of user u (row u of A), ascending — decoded from the bit-packed mask."""
@@ -526,13 +527,28 @@ class SpreadingEngine:
         return At, Q, shift
 
     def general_w(self, item_range: Optional[tuple[int, int]] = None, operands=None,
-                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """G = A^T K_u^-1 A (model/SpreadMethod/model.py:14-27) on the tensor cores (exact int8 fixed point)."""
+                  out: Optional[torch.Tensor] = None, symmetric: Optional[bool] = None) -> torch.Tensor:
+        """G = A^T K_u^-1 A (model/SpreadMethod/model.py:14-27) on the tensor cores (exact int8 fixed point).
+        The full matrix is bitwise symmetric, so by default only the tiles touching its upper triangle are computed
+        (hs_gemm_planes_sym); a column block (item_range, the multi-GPU shard) computes all of its tiles."""
         if self.g_kind != "u8":
             raise LgcnhsError("g_kind must be 'u8'")
         j0, j1 = (0, self.M) if item_range is None else item_range
         At, Q, shift = self.pack_g_operands() if operands is None else operands
-        G = gemm_planes(1, At, Q[:, j0:j1], self.M, j1 - j0, self.U, out=out, scale=2.0 ** (-shift))
+        if symmetric is None:
+            symmetric = item_range is None and os.environ.get("LGCNHS_NO_SYM_G", "0") != "1"
+        if symmetric and item_range is not None:
+            raise LgcnhsError("general_w: the symmetric schedule needs the full matrix")
+        if symmetric:
+            M = self.M
+            if out is None:
+                out = torch.empty((M, _pad(M, 4)), dtype=torch.float32, device=self.dev)[:, :M]
+            check(lib().hs_gemm_planes_sym(_ptr(At), int(At.stride(0)), _ptr(Q), int(Q.stride(1)), int(Q.stride(0)),
+                                           int(Q.shape[0]), M, self.U, _ptr(out), int(out.stride(0)), 2.0 ** (-shift),
+                                           _stream()), "gemm planes (symmetric)")
+            G = out
+        else:
+            G = gemm_planes(1, At, Q[:, j0:j1], self.M, j1 - j0, self.U, out=out, scale=2.0 ** (-shift))
         if item_range is None:
             self.G = G
         return G
@@ -561,7 +577,8 @@ class SpreadingEngine:
         deg = self.ki if diversity else None
         lambdas = [float(x) for x in lambdas]
         sums = torch.zeros((len(lambdas), 6), dtype=torch.float64, device=self.dev)
-        F = torch.empty((self.U, _pad(self.M, 4)), dtype=torch.float32, device=self.dev)[:, : self.M]
+        fuse = layer0 is None and gscore is None and self.can_fuse_topk(k, self.U)   # F never materialised
+        F = None if fuse else torch.empty((self.U, _pad(self.M, 4)), dtype=torch.float32, device=self.dev)[:, : self.M]
         for n, lam in enumerate(lambdas):
             if layer0 is not None:
                 xu, xi, seen = layer0
@@ -602,14 +619,48 @@ class SpreadingEngine:
         u0, u1 = (0, self.U) if user_range is None else user_range
         return gemm_planes(self.w_kind, self.A[u0:u1], self.Wt, u1 - u0, self.M, self.M, out=out, cs=self.col_scale)
 
+    def resource_topk(self, k: int, filtered: bool = True, user_range: Optional[tuple[int, int]] = None,
+                      want_values: bool = True):
+        """top-k of F = A . W for a block of users WITHOUT materialising F: the selection runs in the epilogue of the
+        tensor-core GEMM (hs_resource_topk).  Needs scale() first; k <= 32, more than 128 users, uint8 W planes."""
+        if self.Wt is None:
+            raise LgcnhsError("resource_topk(): scale() has not been called")
+        u0, u1 = (0, self.U) if user_range is None else user_range
+        rows = u1 - u0
+        nbytes = int(lib().hs_resource_topk_scratch_bytes(rows, self.M, self.w_planes))
+        scr = self._topk_scratch
+        if scr is None or scr.numel() < nbytes:
+            scr = self._topk_scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
+        idx = torch.empty((rows, k), dtype=torch.int64, device=self.dev)
+        val = torch.empty((rows, k), dtype=torch.float32, device=self.dev) if want_values else None
+        A = self.A[u0:u1]
+        check(lib().hs_resource_topk(_ptr(A), int(A.stride(0)), _ptr(self.Wt), int(self.Wt.stride(1)),
+                                     int(self.Wt.stride(0)), self.w_planes, rows, self.M, self.M, _ptr(self.col_scale), 1.0,
+                                     _ptr(self.excl.bits) if filtered else 0, self.excl.stride_bits if filtered else 0,
+                                     u0, int(k), _ptr(idx), _ptr(val), _ptr(scr), nbytes, _stream()), "resource_topk")
+        return idx, val
+
+    def can_fuse_topk(self, k: int, rows: int) -> bool:
+        return self.w_kind == 1 and k <= 32 and rows > 128 and os.environ.get("LGCNHS_NO_FUSED_TOPK", "0") != "1"
+
     def recommend(self, lam: float, k: int, filtered: bool = True, gscore: Optional[torch.Tensor] = None,
-                  user_range: Optional[tuple[int, int]] = None, F_out: Optional[torch.Tensor] = None):
-        """lambda -> top-k item ids (U, k) int64 + scores; optional fusion F * gscore."""
+                  user_range: Optional[tuple[int, int]] = None, F_out: Optional[torch.Tensor] = None,
+                  fused: Optional[bool] = None):
+        """lambda -> top-k item ids (U, k) int64 + scores; optional fusion F * gscore.
+        fused (default: whenever possible and no F_out / gscore is asked for): the top-k is selected inside the
+        F-GEMM epilogue and F is never written (resource_topk); otherwise F is materialised and ranked by
+        lgc_topk_rows.  Both give identical lists."""
         if self.G is None:
             self.general_w()
         self.scale(lam)
+        u0, u1 = (0, self.U) if user_range is None else user_range
+        if fused is None:
+            fused = gscore is None and F_out is None and self.can_fuse_topk(k, u1 - u0)
+        if fused:
+            if gscore is not None:
+                raise LgcnhsError("recommend: the fused epilogue has no Hadamard factor; pass fused=False")
+            return self.resource_topk(k, filtered, user_range)
         F = self.resource(user_range, out=F_out)
-        u0 = 0 if user_range is None else user_range[0]
         if gscore is not None:
             check(lib().hs_hadamard(_ptr(F), _ptr(gscore), int(F.shape[0]), int(F.shape[1]), int(F.stride(0)),
                                     int(gscore.stride(0)), _stream()), "hadamard")

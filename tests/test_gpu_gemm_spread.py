@@ -155,3 +155,78 @@ def test_gemm_cta_pair_equals_single_cta(dev, kind, planes, M, N, K):
     finally:
         lib().hs_gemm_use_cta_pair(1)
     assert torch.equal(C1, C2)
+
+
+@pytest.mark.parametrize("name", ["small", "ml-100k", "ml-1m"])
+def test_symmetric_g_schedule_is_bit_identical(dev, name):
+    """hs_gemm_planes_sym computes only the tiles that touch the upper triangle and mirrors them: the result must be
+    bit-identical to the full computation (and to its own transpose), at sizes with ragged last tiles."""
+    from lgcnhs_b200 import ops
+    from lgcnhs_b200.synth import synth_shape
+
+    d = synth_shape(name)
+    eng = ops.SpreadingEngine(d.n_users, d.n_items, torch.from_numpy(d.users).to(dev), torch.from_numpy(d.items).to(dev))
+    operands = eng.pack_g_operands()
+    full = eng.general_w(operands=operands, symmetric=False).clone()
+    out = torch.full((d.n_items, (d.n_items + 3) // 4 * 4), float("nan"), device=dev)[:, : d.n_items]
+    sym = eng.general_w(operands=operands, symmetric=True, out=out)
+    assert not torch.isnan(sym).any()                       # every entry written (directly or by the mirror store)
+    assert torch.equal(sym, full) and torch.equal(sym, sym.T)
+    A = S.interaction_matrix(d.n_users, d.n_items, d.users, d.items)
+    if name != "ml-1m":
+        assert_close(sym, torch.from_numpy(S.get_spreading_general_mat(A)), "symmetric-schedule G vs oracle")
+
+
+@pytest.mark.parametrize("name,k,w_mode", [("small", 10, "u8x4"), ("small", 32, "u8x3"), ("ml-100k", 20, "u8x4"),
+                                           ("ml-100k", 1, "u8x4"), ("ml-1m", 20, "u8x4"), ("ml-1m", 20, "u8x3")])
+def test_fused_resource_topk_equals_unfused(dev, name, k, w_mode):
+    """hs_resource_topk (top-k inside the F-GEMM epilogue, F never written) must return EXACTLY the lists and values of
+    hs_gemm_planes + lgc_topk_rows: same fixed-point arithmetic, same total order (value desc, larger column first)."""
+    from lgcnhs_b200 import ops
+    from lgcnhs_b200.synth import synth_shape
+
+    d = synth_shape(name)
+    tr, va, _ = d.split()
+    sel = np.r_[tr, va]
+    eng = ops.SpreadingEngine(d.n_users, d.n_items, torch.from_numpy(d.users[sel]).to(dev),
+                              torch.from_numpy(d.items[sel]).to(dev), w_mode=w_mode)
+    assert eng.can_fuse_topk(k, d.n_users)
+    for lam in (0.0, 0.3, 1.0):
+        for filtered in (True, False):
+            i0, v0 = eng.recommend(lam, k, filtered=filtered, fused=False)
+            i1, v1 = eng.recommend(lam, k, filtered=filtered, fused=True)
+            assert torch.equal(i0, i1), f"{name} lam={lam} filtered={filtered}: {(i0 != i1).sum().item()} ids differ"
+            assert torch.equal(v0, v1)
+    # a block of users with an offset into the exclusion mask (the multi-GPU user-block shard)
+    u0, u1 = d.n_users // 3, d.n_users // 3 + max(129, d.n_users // 2)
+    u1 = min(u1, d.n_users)
+    if u1 - u0 > 128:
+        ia, va_ = eng.recommend(0.3, k, user_range=(u0, u1), fused=False)
+        ib, vb = eng.recommend(0.3, k, user_range=(u0, u1), fused=True)
+        assert torch.equal(ia, ib) and torch.equal(va_, vb)
+    # against the oracle (tie-aware) on the small shapes
+    if name != "ml-1m":
+        from _parity import assert_topk_parity
+        A = S.interaction_matrix(d.n_users, d.n_items, d.users[sel], d.items[sel])
+        F = S.get_resource(A, S.hybrids(A, S.get_spreading_general_mat(A), 0.3))
+        ref_idx, _ = S.recommend_fast(F, A, k)
+        got, _ = eng.recommend(0.3, k, fused=True)
+        assert_topk_parity(got.cpu().numpy(), ref_idx, F, f"fused resource top-k vs oracle ({name})", seen_mask=A > 0,
+                           min_checked=0.5)
+
+
+def test_fused_resource_topk_few_selectable_items(dev):
+    """Rows with fewer than k selectable items get (-1, -inf) padding, exactly like lgc_topk_rows."""
+    from lgcnhs_b200 import ops
+
+    g = np.random.default_rng(1)
+    U, M = 200, 40
+    dense = g.random((U, M)) < 0.6
+    dense[:5] = True                                        # five users have seen everything
+    dense[5, : M - 3] = True                                # one user has three items left
+    u, i = np.nonzero(dense)
+    eng = ops.SpreadingEngine(U, M, torch.from_numpy(u).to(dev), torch.from_numpy(i).to(dev))
+    i0, v0 = eng.recommend(0.5, 20, fused=False)
+    i1, v1 = eng.recommend(0.5, 20, fused=True)
+    assert torch.equal(i0, i1) and torch.equal(v0, v1)
+    assert (i1[:5] == -1).all() and (i1[5, 3:] == -1).all() and (i1[5, :3] >= M - 3).all()
