@@ -366,6 +366,22 @@ def spreading_leg(dev, steps: int, warmup: int):
         eng.resource(out=F)
     ev[5].record()
     torch.cuda.synchronize()
+    # the same lambda step with the top-k selected inside the F-GEMM epilogue (F never written), and that kernel alone
+    evf = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    for lam in lams[:warmup]:
+        eng.recommend(float(lam), 20)
+    torch.cuda.synchronize()
+    evf[0].record()
+    for lam in lams[warmup:]:
+        eng.recommend(float(lam), 20)
+    evf[1].record()
+    evf[2].record()
+    for _ in range(steps):
+        eng.resource_topk(20)
+    evf[3].record()
+    torch.cuda.synchronize()
+    t_step_fused = evf[0].elapsed_time(evf[1]) / steps * 1e-3
+    t_ftopk = evf[2].elapsed_time(evf[3]) / steps * 1e-3
     # lambda sweep as findLambda.py runs it: per lambda scale + F + filtered top-20 + the six metrics, one D2H at the end
     te = d.split()[2]
     test_pos = ops.seen_csr(torch.from_numpy(d.users[te]).to(dev), torch.from_numpy(d.items[te]).to(dev), U, M)
@@ -395,8 +411,12 @@ def spreading_leg(dev, steps: int, warmup: int):
                    "operand_pack_ms": round(t_pack * 1e3, 4)},
         "f_gemm": {"ms": round(t_f * 1e3, 4), "tflops": round(flops / t_f / 1e12, 2),
                    "kind": "u8 x4 digit planes of per-column fixed-point W, exact int32 accumulate (w_mode u8x4)"},
-        "lambda_step": {"ms": round(t_step * 1e3, 4), "users_per_s": round(U / t_step, 1),
-                        "what": "scale_w + F=A.W + filtered top-20, per lambda"},
+        "lambda_step": {"ms": round(t_step_fused * 1e3, 4), "users_per_s": round(U / t_step_fused, 1),
+                        "what": "scale_w + fused (F=A.W -> filtered top-20 in the GEMM epilogue, F never written), per lambda",
+                        "resource_topk_ms": round(t_ftopk * 1e3, 4),
+                        "resource_topk_tflops": round(flops / t_ftopk / 1e12, 2),
+                        "unfused_ms": round(t_step * 1e3, 4),
+                        "unfused_what": "scale_w + F=A.W materialised + lgc_topk_rows (round-1 path, identical lists)"},
         "lambda_sweep": {"ms_per_lambda": round(t_sweep * 1e3, 4), "users_per_s": round(U / t_sweep, 1), "n_lambda": len(sweep_l),
                          "what": "findLambda.py pattern, wall clock: per lambda scale_w + F=A.W + filtered top-20 + P/R/F1/NDCG/H/I "
                                  "on the device (co-occurrence GEMM once), one device->host copy for the whole sweep",

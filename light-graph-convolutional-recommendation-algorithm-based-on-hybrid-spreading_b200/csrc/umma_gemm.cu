@@ -505,6 +505,24 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
         sel_thr = 0ull; sel_thr_f = -INFINITY; sel_cnt = 0;
         sel_buf = p.cand + ((size_t)(row_ok ? row : 0) * p.segs + ts.seg) * kCandCap;
       }
+      // EPI 1: the exclusion bits of this row for the tile's NB columns, fetched BEFORE waiting for the accumulator so
+      // that their latency hides behind the tile's MMAs (a dependent global load per surviving value would serialise
+      // the first tiles of an item, whose threshold is still -inf)
+      constexpr int MW = (NB + 31) / 32;
+      uint32_t mbits[MW];
+#pragma unroll
+      for (int i = 0; i < MW; ++i) mbits[i] = 0u;
+      if (EPI == 1 && p.excl && row_ok) {
+        const long long b0 = (p.excl_row0 + row) * p.excl_stride + (long long)n_blk * NB;
+        const long long last_word = ((p.excl_row0 + row) * p.excl_stride + p.N - 1) >> 5;   // last word holding a bit of this row
+        const long long w0 = b0 >> 5;
+        const int sh = (int)(b0 & 31);
+        uint32_t raw[MW + 1];
+#pragma unroll
+        for (int i = 0; i <= MW; ++i) raw[i] = (w0 + i <= last_word) ? __ldg(p.excl + w0 + i) : 0u;
+#pragma unroll
+        for (int i = 0; i < MW; ++i) mbits[i] = __funnelshift_r(raw[i], raw[i + 1], sh);
+      }
       float run[NB];
       for (int ch = 0; ch < n_chunks; ++ch, ++it) {
         const int acc = it & 1;
@@ -573,14 +591,8 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
                   const int64_t col = col0 + j;
                   if (out[j] >= sel_thr_f && col < p.N) {
                     const unsigned long long key = make_key(float_key(out[j]), (uint32_t)col);
-                    if (key > sel_thr) {
-                      bool ex = false;
-                      if (p.excl) {
-                        const long long b = (p.excl_row0 + row) * p.excl_stride + col;
-                        ex = (__ldg(p.excl + (b >> 5)) >> (b & 31)) & 1u;
-                      }
-                      if (!ex) sel_buf[sel_cnt++] = key;
-                    }
+                    const bool ex = (mbits[(c0 + j) >> 5] >> ((c0 + j) & 31)) & 1u;
+                    if (key > sel_thr && !ex) sel_buf[sel_cnt++] = key;
                   }
                 }
               }

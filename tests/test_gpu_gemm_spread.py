@@ -224,6 +224,7 @@ def test_fused_resource_topk_few_selectable_items(dev):
     dense = g.random((U, M)) < 0.6
     dense[:5] = True                                        # five users have seen everything
     dense[5, : M - 3] = True                                # one user has three items left
+    dense[5, M - 3:] = False
     u, i = np.nonzero(dense)
     eng = ops.SpreadingEngine(U, M, torch.from_numpy(u).to(dev), torch.from_numpy(i).to(dev))
     i0, v0 = eng.recommend(0.5, 20, fused=False)
