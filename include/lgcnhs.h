@@ -202,6 +202,18 @@ int lgc_score_topk(const float* Xu, const float* Xi, int64_t u0, int64_t u1, int
                    int32_t dim, const int32_t* seen_ptr, const int32_t* seen_idx, float fill,
                    int32_t exclude_seen, const float* mul, int64_t ldmul, int32_t k,
                    int64_t* out_idx, float* out_val, lgc_stream_t stream);
+/* Same contract on the TENSOR CORES (tcgen05 kind::tf32, 3xTF32 split of both operands: hi*lo + lo*hi + hi*hi, fp32
+ * accumulate in TMEM): ~10x the throughput of the fp32-FMA kernel above.  Scores agree with an fp32 SGEMM to ~1e-6
+ * relative (inside the 1e-5 tolerance); ids are identical except at float near-ties.  Xu is the FULL (n_users_total,
+ * dim) table, users [u0, u1) are ranked; mul (may be null) is (u1-u0, ldmul).  dim in {32, 64}, k <= 32.
+ * workspace: lgc_score_topk_tc_workspace_bytes(), 256-byte aligned (hi/lo planes of both tables + candidate
+ * buffers).  Replaces the same reference lines as lgc_score_topk. */
+int64_t lgc_score_topk_tc_workspace_bytes(int64_t n_users_total, int64_t n_items, int64_t rows, int32_t dim);
+int lgc_score_topk_tc(const float* Xu, const float* Xi, int64_t n_users_total, int64_t u0, int64_t u1,
+                      int64_t n_items, int32_t dim, const int32_t* seen_ptr, const int32_t* seen_idx,
+                      float fill, int32_t exclude_seen, const float* mul, int64_t ldmul, int32_t k,
+                      int64_t* out_idx, float* out_val, void* workspace, int64_t workspace_bytes,
+                      lgc_stream_t stream);
 /* Device-side barrier over peer memory (replaces one NCCL all-reduce per propagation layer in the multi-GPU
  * p2p mode).  Every rank owns local_flags[n_peers] in IPC-mapped memory, zero-initialised; the call publishes
  * `epoch` into peer_flags_host[p][my_rank] for every p and returns (stream-ordered) once local_flags[q] >= epoch

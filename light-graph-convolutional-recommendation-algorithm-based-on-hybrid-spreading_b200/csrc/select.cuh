@@ -155,4 +155,40 @@ __device__ __forceinline__ int warp_select(unsigned long long* buf, int cnt, int
   return base;
 }
 
+// ---- fused top-k epilogues of the tensor-core kernels (umma_gemm.cu, score_topk_tc.cu) ----
+// Every (row, segment) owns a candidate buffer of kCandCap keys in global scratch, written by ONE epilogue thread;
+// a final warp-per-row kernel merges the segments' buffers and writes the k best, sorted (value descending, ties ->
+// larger column first).
+constexpr int kCandCap = 128;   // k <= 32, at most 64-80 values offered between two overflow checks
+constexpr int kMergeWarps = 8;
+
+template <int CAPC>
+__global__ void __launch_bounds__(kMergeWarps * 32)
+topk_merge_kernel(const unsigned long long* __restrict__ cand, const int* __restrict__ cand_cnt, int64_t n_rows, int segs,
+                  int k, int64_t* __restrict__ out_idx, float* __restrict__ out_val) {
+  constexpr int CAPM = 2 * CAPC;
+  __shared__ unsigned long long s_buf[kMergeWarps][CAPM];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t row = (int64_t)blockIdx.x * kMergeWarps + w;
+  if (row >= n_rows) return;
+  unsigned long long* buf = s_buf[w];
+  unsigned long long thr;
+  int cur = 0;
+  for (int sg = 0; sg < segs; ++sg) {
+    int c = cand_cnt[(size_t)row * segs + sg];
+    c = c < CAPC ? c : CAPC;
+    if (cur + c > CAPM) cur = warp_select<CAPM / 32>(buf, cur, k, lane, &thr);
+    const unsigned long long* src = cand + ((size_t)row * segs + sg) * CAPC;
+    for (int i = lane; i < c; i += 32) buf[cur + i] = src[i];
+    cur += c;
+    __syncwarp();
+  }
+  const int kept = warp_compact<CAPM / 32>(buf, cur, k, lane, &thr);
+  for (int i = lane; i < k; i += 32) {
+    const unsigned long long key = buf[i];
+    out_idx[row * k + i] = i < kept ? (int64_t)(uint32_t)(key & 0xffffffffull) : -1;
+    if (out_val) out_val[row * k + i] = i < kept ? key_float((uint32_t)(key >> 32)) : -INFINITY;
+  }
+}
+
 }  // namespace lgc

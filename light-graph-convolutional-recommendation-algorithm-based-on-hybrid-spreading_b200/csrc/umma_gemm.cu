@@ -60,7 +60,6 @@ struct GemmParams {
   int* cand_cnt;                 // [M * segs]
 };
 
-constexpr int kCandCap = 128;    // per (row, segment) candidate buffer of the fused top-k epilogue (k <= 32)
 
 struct TileSched {
   int m, n, seg, n_end;
@@ -306,58 +305,6 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constan
 //   * both CTAs run 4 epilogue warps on their own 128 TMEM lanes and arrive remotely on the leader's
 //     "accumulator empty" barrier (count 8).
 // ================================================================================================
-constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared::cluster address of the even CTA of a pair
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // remote (or local) arrive on the even CTA
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
-}
-__device__ __forceinline__ void tma2_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma2_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tc_commit2_mc(uint64_t* bar) {  // arrive on the same barrier offset in BOTH CTAs
-  const unsigned short mask = 3;
-  asm volatile(
-      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-          smem_u32(bar)),
-      "h"(mask)
-      : "memory");
-}
-template <int KIND>
-__device__ __forceinline__ void mma2_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                        uint32_t accumulate) {
-  if (KIND == 0) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-  }
-}
-
 // each CTA stages 16 KB of A + <= 16 KB of B per K-block, so six stages fit where the single-CTA kernel has four
 constexpr int kPStages = 6;
 constexpr int kPBStage = 128 * kKBytes;  // 16 KB
@@ -637,37 +584,6 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
   }
 }
 
-// Final step of the fused top-k: one warp per row merges the candidate lists its `segs` segments left behind
-// (<= kCandCap keys each) and writes the k best, sorted (value descending, ties -> larger column first).
-constexpr int kMergeWarps = 8;
-__global__ void __launch_bounds__(kMergeWarps * 32)
-resource_topk_merge_kernel(const unsigned long long* __restrict__ cand, const int* __restrict__ cand_cnt, int64_t n_rows,
-                           int segs, int k, int64_t* __restrict__ out_idx, float* __restrict__ out_val) {
-  constexpr int CAPM = 2 * kCandCap;
-  __shared__ unsigned long long s_buf[kMergeWarps][CAPM];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t row = (int64_t)blockIdx.x * kMergeWarps + w;
-  if (row >= n_rows) return;
-  unsigned long long* buf = s_buf[w];
-  unsigned long long thr;
-  int cur = 0;
-  for (int sg = 0; sg < segs; ++sg) {
-    int c = cand_cnt[(size_t)row * segs + sg];
-    c = c < kCandCap ? c : kCandCap;
-    if (cur + c > CAPM) cur = warp_select<CAPM / 32>(buf, cur, k, lane, &thr);
-    const unsigned long long* src = cand + ((size_t)row * segs + sg) * kCandCap;
-    for (int i = lane; i < c; i += 32) buf[cur + i] = src[i];
-    cur += c;
-    __syncwarp();
-  }
-  const int kept = warp_compact<CAPM / 32>(buf, cur, k, lane, &thr);
-  for (int i = lane; i < k; i += 32) {
-    const unsigned long long key = buf[i];
-    out_idx[row * k + i] = i < kept ? (int64_t)(uint32_t)(key & 0xffffffffull) : -1;
-    if (out_val) out_val[row * k + i] = i < kept ? key_float((uint32_t)(key >> 32)) : -INFINITY;
-  }
-}
-
 static int g_use_pair = 1;   // cta_group::2 kernel when the problem has at least one 256-row tile
 static int g_chunk_kb = 8;  // K-blocks (of 64 bf16) per TMEM accumulation chunk, see header comment
 
@@ -874,9 +790,9 @@ static int gemm_planes_impl(int32_t kind, const void* A, int64_t lda, const void
     if (!launched) LGC_FAIL(LGC_ERR_UNSUPPORTED, "gemm: kind %d / %d planes not available in this mode", kind, planes);
     LGC_LAUNCH_CHECK("umma_gemm_pair_kernel");
     if (mode == 2) {
-      resource_topk_merge_kernel<<<(unsigned)ceil_div(M, kMergeWarps), kMergeWarps * 32, 0, stream>>>(
+      topk_merge_kernel<kCandCap><<<(unsigned)ceil_div(M, kMergeWarps), kMergeWarps * 32, 0, stream>>>(
           p.cand, p.cand_cnt, M, p.segs, topk->k, topk->out_idx, topk->out_val);
-      LGC_LAUNCH_CHECK("resource_topk_merge_kernel");
+      LGC_LAUNCH_CHECK("topk_merge_kernel");
     }
     return LGC_OK;
   }

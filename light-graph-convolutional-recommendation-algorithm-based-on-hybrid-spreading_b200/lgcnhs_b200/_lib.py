@@ -43,6 +43,9 @@ _SIGS = {
     "lgc_score_block": (C.c_int, [_p, _p, _i64, _i64, _i64, _i32, _p, _p, _f32, _p, _i64, _p]),
     "lgc_topk_rows": (C.c_int, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i32, _p, _p, _p]),
     "lgc_score_topk": (C.c_int, [_p, _p, _i64, _i64, _i64, _i32, _p, _p, _f32, _i32, _p, _i64, _i32, _p, _p, _p]),
+    "lgc_score_topk_tc_workspace_bytes": (_i64, [_i64, _i64, _i64, _i32]),
+    "lgc_score_topk_tc": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _i32, _p, _p, _f32, _i32, _p, _i64, _i32, _p, _p, _p, _i64,
+                                    _p]),
     "lgc_negative_sample": (C.c_int, [_p, _p, _i64, _p, _i64, _p, _p, _i64, _i64, _i32, C.c_uint64, _p, _p, _p, _p, _p]),
     "lgc_metrics_scratch_bytes": (_i64, [_i64]),
     "lgc_metrics_topk": (C.c_int, [_p, _i64, _i32, _i64, _p, _p, _p, _i64, _p, _p, _p, _p]),

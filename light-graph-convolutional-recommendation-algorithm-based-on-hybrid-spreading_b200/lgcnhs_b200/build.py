@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 CSRC = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "csrc"))
 LIB_PATH = os.path.join(CSRC, "liblgcnhs.so")
-SOURCES = ["capi.cu", "graph.cu", "spmm.cu", "train_ops.cu", "score_topk.cu", "spread_ops.cu", "umma_gemm.cu", "metrics.cu", "sampler.cu", "probe.cu"]
+SOURCES = ["capi.cu", "graph.cu", "spmm.cu", "train_ops.cu", "score_topk.cu", "score_topk_tc.cu", "spread_ops.cu", "umma_gemm.cu", "metrics.cu", "sampler.cu", "probe.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -322,11 +322,21 @@ def score_block(Xu: torch.Tensor, Xi: torch.Tensor, u0: int, u1: int, seen: Opti
     return out
 
 
+_tc_ws: dict = {}
+
+
 def score_topk(Xu: torch.Tensor, Xi: torch.Tensor, k: int, seen: Optional[tuple] = None, fill: float = -1024.0,
                exclude_seen: bool = False, mul: Optional[torch.Tensor] = None, u0: int = 0, u1: Optional[int] = None,
-               want_values: bool = True):
+               want_values: bool = True, precise: Optional[bool] = None):
     """Fused  top-k_i ( (seen ? fill : <Xu[u], Xi[i]>) * mul[u, i] )  for users [u0, u1): the score matrix is never
-    materialised (reference: matmul + index_put(-1024) + topk, model/LightGCN/recommend.py:86-114)."""
+    materialised (reference: matmul + index_put(-1024) + topk, model/LightGCN/recommend.py:86-114).
+
+    Two kernels behind one contract:
+      * tensor cores (default when dim in {32, 64}, k <= 32 and more than 128 users): tcgen05 kind::tf32 with a 3xTF32
+        split of both operands (lgc_score_topk_tc) — scores within ~1e-6 relative of an fp32 SGEMM, ids identical
+        except at float near-ties;
+      * precise=True (or LGCNHS_SCORE_FP32=1, or any shape the tensor-core kernel does not take): packed fp32 FMA
+        (lgc_score_topk), bit-identical to the scalar fp32 dot product."""
     Xu = _req(Xu, torch.float32, "Xu")
     Xi = _req(Xi, torch.float32, "Xi")
     M, dim = int(Xi.shape[0]), int(Xi.shape[1])
@@ -337,6 +347,18 @@ def score_topk(Xu: torch.Tensor, Xi: torch.Tensor, k: int, seen: Optional[tuple]
             raise LgcnhsError("score_topk: mul must be a CUDA fp32 (u1-u0, n_items) matrix with unit column stride")
     idx = torch.empty((u1 - u0, k), dtype=torch.int64, device=Xu.device)
     val = torch.empty((u1 - u0, k), dtype=torch.float32, device=Xu.device) if want_values else None
+    if precise is None:
+        precise = os.environ.get("LGCNHS_SCORE_FP32", "0") == "1"
+    if not precise and dim in (32, 64) and k <= 32 and (u1 - u0) > 128:
+        n_total = int(Xu.shape[0])
+        nbytes = int(lib().lgc_score_topk_tc_workspace_bytes(n_total, M, u1 - u0, dim))
+        ws = _tc_ws.get(Xu.device)
+        if ws is None or ws.numel() < nbytes:
+            ws = _tc_ws[Xu.device] = torch.empty(nbytes, dtype=torch.uint8, device=Xu.device)
+        check(lib().lgc_score_topk_tc(_ptr(Xu), _ptr(Xi), n_total, u0, u1, M, dim, _ptr(sp), _ptr(si), float(fill),
+                                      int(exclude_seen), _ptr(mul), int(mul.stride(0)) if mul is not None else 0, int(k),
+                                      _ptr(idx), _ptr(val), _ptr(ws), nbytes, _stream()), "score_topk_tc")
+        return idx, val
     check(lib().lgc_score_topk(_ptr(Xu), _ptr(Xi), u0, u1, M, dim, _ptr(sp), _ptr(si), float(fill), int(exclude_seen),
                                _ptr(mul), int(mul.stride(0)) if mul is not None else 0, int(k), _ptr(idx), _ptr(val),
                                _stream()), "score_topk")

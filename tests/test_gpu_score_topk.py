@@ -141,7 +141,7 @@ def test_score_topk_equals_unfused(dev, U, M, dim, k):
     seen = ops.seen_csr(su.to(dev), si.to(dev), U, M)
     dense = ops.score_block(uw.to(dev), iw.to(dev), 0, U, seen)
     ridx, rval = ops.topk_rows(dense, k)
-    idx, val = ops.score_topk(uw.to(dev), iw.to(dev), k, seen)
+    idx, val = ops.score_topk(uw.to(dev), iw.to(dev), k, seen, precise=True)
     assert torch.equal(val, rval) and torch.equal(idx, ridx)
     # the CPU statement of the reference rule
     ref = uw @ iw.T
@@ -150,7 +150,7 @@ def test_score_topk_equals_unfused(dev, U, M, dim, k):
     assert_close(val, rv, "fused top-k scores")
     # a user sub-range with an odd offset
     if U > 70:
-        idx2, val2 = ops.score_topk(uw.to(dev), iw.to(dev), k, seen, u0=37, u1=U - 5)
+        idx2, val2 = ops.score_topk(uw.to(dev), iw.to(dev), k, seen, u0=37, u1=U - 5, precise=True)
         assert torch.equal(idx2, ridx[37:U - 5]) and torch.equal(val2, rval[37:U - 5])
 
 
@@ -166,7 +166,7 @@ def test_score_topk_adversarial_orders(dev):
     uw[1::3, 0] = -1.0                                  # decreasing rows
     uw[2::3, 0] = 0.0                                   # all-equal rows
     iw[:, 0] = torch.arange(M, dtype=torch.float32) / M
-    idx, val = ops.score_topk(uw.to(dev), iw.to(dev), k)
+    idx, val = ops.score_topk(uw.to(dev), iw.to(dev), k, precise=True)
     ref = uw @ iw.T
     rv, _ = torch.topk(ref, k)
     assert torch.equal(val.cpu(), rv)
@@ -187,7 +187,7 @@ def test_score_topk_fused_hadamard_and_exclusion(dev):
     F = torch.rand(U, M, generator=g)
     F[F < 0.5] = 0.0
     seen = ops.seen_csr(su.to(dev), si.to(dev), U, M)
-    idx, val = ops.score_topk(uw.to(dev), iw.to(dev), k, seen, exclude_seen=True, mul=F.to(dev))
+    idx, val = ops.score_topk(uw.to(dev), iw.to(dev), k, seen, exclude_seen=True, mul=F.to(dev), precise=True)
     # unfused device path: masked score, Hadamard, filtered top-k
     dense = ops.score_block(uw.to(dev), iw.to(dev), 0, U, seen) * F.to(dev)
     excl = ops.ExclusionMask.from_csr(seen, U, M)
@@ -220,7 +220,111 @@ def test_score_topk_large_user_tiles(dev, k, threads):
     default = 512
     lib().lgc_score_topk_config(threads)
     try:
-        idx, val = ops.score_topk(uw.to(dev), iw.to(dev), k, seen)
+        idx, val = ops.score_topk(uw.to(dev), iw.to(dev), k, seen, precise=True)
     finally:
         lib().lgc_score_topk_config(default)
     assert torch.equal(val, rval) and torch.equal(idx, ridx)
+
+
+# ------------------------------------------------------------------------------------------
+# the same contract on the tensor cores (lgc_score_topk_tc: tcgen05 kind::tf32, 3xTF32 split)
+# ------------------------------------------------------------------------------------------
+def _tc_check(val, idx, ref64, k, what, seen_mask=None):
+    """Tolerance of the tensor-core path (north_star): score at rank within 1e-5 relative (+1e-7 of the largest ranked
+    score), ids identical except at float near-ties, no excluded id."""
+    from _parity import assert_topk_parity
+
+    S = ref64.numpy().copy()
+    if seen_mask is not None:
+        S[seen_mask] = -np.inf
+    rv, ri = torch.topk(torch.from_numpy(S), k)
+    Sf = ref64.numpy()
+    frac = assert_topk_parity(idx.cpu().numpy(), ri.numpy(), Sf, what, seen_mask=seen_mask, min_checked=0.6, tol_mult=1.0)
+    got_v = val.cpu().double().numpy()
+    want = np.take_along_axis(Sf, idx.cpu().numpy(), axis=1)
+    scale = np.abs(want).max()
+    assert (np.abs(got_v - want) <= 1e-5 * np.abs(want) + 1e-7 * scale).all(), \
+        f"{what}: returned values off by {np.abs(got_v - want).max():.3e}"
+    return frac
+
+
+@pytest.mark.parametrize("U,M,dim,k", [(943, 1682, 64, 20), (300, 3706, 64, 10), (129, 700, 64, 32), (1000, 513, 32, 20),
+                                       (6040, 3706, 64, 20), (2000, 26744, 64, 1)])
+def test_score_topk_tensor_core_matches_fp64(dev, U, M, dim, k):
+    """fill(-1024) semantics of recommend.py:86-114 on the tensor cores vs the float64 statement of the rule, and vs the
+    fp32-FMA kernel (ids equal outside near-ties)."""
+    from lgcnhs_b200 import ops
+
+    uw, iw, su, si = _rand_problem(U, M, dim, U * 3 + M, 30 * U)
+    seen = ops.seen_csr(su.to(dev), si.to(dev), U, M)
+    idx, val = ops.score_topk(uw.to(dev), iw.to(dev), k, seen)                   # tensor-core path (U > 128, k <= 32)
+    ref = uw.double() @ iw.double().T
+    ref[su, si] = -1024.0
+    _tc_check(val, idx, ref, k, f"tc score_topk {U}x{M}x{dim}")
+    pidx, pval = ops.score_topk(uw.to(dev), iw.to(dev), k, seen, precise=True)
+    assert (idx == pidx).float().mean() > 0.995
+    assert torch.allclose(val, pval, rtol=1e-5, atol=1e-7 * float(pval.abs().max()))
+    # user sub-range with an odd offset: rows are independent, so the block equals the slice bit for bit
+    idx2, val2 = ops.score_topk(uw.to(dev), iw.to(dev), k, seen, u0=37, u1=U - 5)
+    if U - 42 > 128:
+        assert torch.equal(idx2, idx[37:U - 5]) and torch.equal(val2, val[37:U - 5])
+
+
+def test_score_topk_tensor_core_seen_rule_and_ties(dev):
+    """Seen pairs inside the top-k region: users with so few unseen items that -1024 entries must appear in the list
+    (reference quirk: masked pairs stay in the ranking), exact ties (duplicate item rows -> larger id first), and the
+    exclusion variant."""
+    from lgcnhs_b200 import ops
+
+    U, M, k = 300, 600, 20
+    g = torch.Generator().manual_seed(4)
+    uw = torch.empty(U, 64).normal_(std=0.1, generator=g)
+    iw = torch.empty(M, 64).normal_(std=0.1, generator=g)
+    iw[301] = iw[300]                                       # exact tie for every user
+    dense_seen = torch.rand(U, M, generator=g) < 0.2
+    dense_seen[:4, 5:] = True                               # four users have only items 0..4 unseen
+    su, si = torch.nonzero(dense_seen, as_tuple=True)
+    seen = ops.seen_csr(su.to(dev), si.to(dev), U, M)
+    idx, val = ops.score_topk(uw.to(dev), iw.to(dev), k, seen)
+    ref = uw.double() @ iw.double().T
+    ref[su, si] = -1024.0
+    rv, ri = torch.topk(ref, k)
+    assert torch.allclose(val.cpu().double(), rv, rtol=1e-5, atol=1e-6)
+    assert (val[:4, 5:] == -1024.0).all() and (val[:4, :5] > -1024.0).all()
+    both = ((idx.cpu() == 300) | (idx.cpu() == 301)).sum(1) == 2
+    pos300 = (idx.cpu() == 300).float().argmax(1)
+    pos301 = (idx.cpu() == 301).float().argmax(1)
+    assert (pos301[both] < pos300[both]).all() and both.any()       # equal scores: the larger id ranks first
+    # exclusion variant + multiplier (fusion F1)
+    F = torch.rand(U, M, generator=g)
+    F[F < 0.5] = 0.0
+    eidx, eval_ = ops.score_topk(uw.to(dev), iw.to(dev), k, seen, exclude_seen=True, mul=F.to(dev))
+    Fn = ref.clone()
+    Fn[su, si] = 0.0
+    Fn = (uw.double() @ iw.double().T) * F.double()
+    mask = dense_seen.numpy()
+    _tc_check(eval_[4:], eidx[4:], Fn[4:], k, "tc fused Hadamard + exclusion", seen_mask=mask[4:])
+    assert (eidx[:4, 5:] == -1).all()                       # fewer than k selectable items -> (-1, -inf) padding
+    assert not dense_seen[torch.arange(U)[:, None].expand(-1, k)[eidx.cpu() >= 0], eidx.cpu()[eidx.cpu() >= 0]].any()
+
+
+def test_score_topk_tensor_core_adversarial_orders(dev):
+    """Scores increasing with the item id (every tile beats the threshold: maximum compaction rate), decreasing, and
+    all-equal rows (pure tie-break), with values exactly representable so that the 3xTF32 split is exact."""
+    from lgcnhs_b200 import ops
+
+    U, M, k = 300, 4000, 20
+    uw = torch.zeros(U, 64)
+    iw = torch.zeros(M, 64)
+    uw[:, 0] = 1.0
+    uw[1::3, 0] = -1.0
+    uw[2::3, 0] = 0.0
+    iw[:, 0] = torch.arange(M, dtype=torch.float32) / 4096.0
+    idx, val = ops.score_topk(uw.to(dev), iw.to(dev), k)
+    ref = uw @ iw.T
+    rv, _ = torch.topk(ref, k)
+    assert torch.equal(val.cpu(), rv)
+    idx = idx.cpu()
+    assert idx[0].tolist() == list(range(M - 1, M - 1 - k, -1))
+    assert idx[1].tolist() == list(range(0, k))
+    assert idx[2].tolist() == list(range(M - 1, M - 1 - k, -1))
