@@ -19,7 +19,8 @@
 //                              tile's items (128 rows x (hi + lo) = 64 KB) into a 2-stage ring
 //   warp 1      MMA issuer   : leader CTA only, 24 MMAs (M 256 x N 256 x K 8) per tile into a double-buffered TMEM
 //                              accumulator (2 x 256 columns)
-//   warps 2..5  epilogue     : one thread per user row: tcgen05.ld 16 scores at a time -> optional multiplier (fusion)
+//   warps 2..17 epilogue     : 4 threads per user row (one per 64-column quarter of the tile): tcgen05.ld 16 scores at a
+//                              time -> ONE compare of their maximum against the row's shared threshold -> (fusion: multiplier)
 //                              -> seen-pair rule through a CURSOR into the row's sorted seen list (the tiles of an item
 //                              advance monotonically through the item ids, so no search and no mask matrix is needed)
 //                              -> one float compare against the row's current k-th best -> survivors appended to the
@@ -34,6 +35,15 @@ namespace umma {
 constexpr int kTcTileN = 256;                       // items per tile (MMA N)
 constexpr int kTcKbBytes = 128 * 128;               // one K-block tile: 128 rows x 128 B (32 fp32), SWIZZLE_128B
 constexpr int kTcStages = 2;
+// Epilogue: 16 warps = 4 TMEM lane quarters x 4 COLUMN quarters of the tile.  TMEM reads return 64 B/clk and the MMAs
+// of a tile take ~3 k cycles, so the selection must cost only a few instructions per score: with one warp per
+// scheduler the 4-warp version was issue-bound at ~16 k cycles per tile.  Four threads share a user row, each ranks
+// its own 64 columns of every tile into its own candidate buffer (merged at the end like segments) and they share
+// the row's pruning threshold through shared memory.
+constexpr int kTcColParts = 4;
+constexpr int kTcEpiWarps = 4 * kTcColParts;
+constexpr int kTcThreads = 64 + 32 * kTcEpiWarps;   // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
+constexpr int kTcColsPerPart = kTcTileN / kTcColParts;   // 64
 
 struct ScoreTcParams {
   int64_t u0, u1;                                   // users [u0, u1) of the embedding table
@@ -68,7 +78,7 @@ __global__ void split_tf32_kernel(const float* __restrict__ X, int64_t n, float*
 }
 
 template <int KB /* K-blocks of 32 fp32: dim = 32 * KB */, bool MUL>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_constant__ CUtensorMap tmapI,
                      const ScoreTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -85,6 +95,9 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_con
   uint64_t* tfull = bars + 2 + 2 * kTcStages;    // [2] per CTA
   uint64_t* tempty = bars + 4 + 2 * kTcStages;   // [2] leader
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 2 * kTcStages);
+  // value key (monotone uint32 of the fp32 score) of the best known k-th score of each of the CTA's 128 user rows:
+  // the maximum over the four column quarters' own thresholds — a score below it cannot be in the row's top-k
+  uint32_t* s_row_thr = tmem_slot + 4;   // [128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -96,7 +109,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_con
     mbar_init(a_full, 2);
     mbar_init(a_empty, 1);
     for (int s = 0; s < kTcStages; ++s) { mbar_init(&b_full[s], 2); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 2 * kTcEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapU) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapI) : "memory");
@@ -204,20 +217,26 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_con
       }
     }
   } else {
-    // ------------------------------ epilogue (warps 2..5, both CTAs) ------------------------------
-    const int q = warp & 3;
+    // ------------------------------ epilogue (warps 2..17, both CTAs) ------------------------------
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int cpart = (warp - 2) >> 2;            // column quarter of every tile this warp ranks
+    const int rloc = q * 32 + lane;               // row inside the CTA's 128
     int it = 0;
     for (long long w = cluster_id; w < n_work; w += n_clusters) {
       const int m_blk = (int)(w / p.segs), seg = (int)(w % p.segs);
       const int n0 = (int)((long long)seg * p.tiles_n / p.segs), n1 = (int)((long long)(seg + 1) * p.tiles_n / p.segs);
       if (n1 <= n0) continue;
-      const int64_t lrow = (int64_t)m_blk * 256 + (int64_t)rank * 128 + q * 32 + lane;   // row inside [0, u1-u0)
+      const int64_t lrow = (int64_t)m_blk * 256 + (int64_t)rank * 128 + rloc;   // row inside [0, u1-u0)
       const int64_t urow = p.u0 + lrow;
       const bool row_ok = urow < p.u1;
       unsigned long long sel_thr = 0ull;
-      float sel_thr_f = -INFINITY;
       int sel_cnt = 0;
-      unsigned long long* sel_buf = p.cand + ((size_t)(row_ok ? lrow : 0) * p.segs + seg) * kCandCap;
+      const int vseg = seg * kTcColParts + cpart;                               // (segment, column quarter) = merge unit
+      unsigned long long* sel_buf = p.cand + ((size_t)(row_ok ? lrow : 0) * (p.segs * kTcColParts) + vseg) * kCandCap;
+      // all epilogue warps of the CTA start the item together: reset the shared row thresholds
+      asm volatile("bar.sync 1, %0;" ::"r"(32 * kTcEpiWarps) : "memory");
+      if (cpart == 0) s_row_thr[rloc] = 0u;
+      asm volatile("bar.sync 1, %0;" ::"r"(32 * kTcEpiWarps) : "memory");
       // cursor into the row's sorted seen list: first entry >= the segment's first item
       int s_cur = 0, s_end = 0;
       if (p.seen_ptr && row_ok) {
@@ -239,75 +258,87 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_con
       for (int n = n0; n < n1; ++n, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
+        // pruning threshold of this tile: the row's best known k-th score over all four column quarters (rows past
+        // the end never pass)
+        const uint32_t tk = s_row_thr[rloc];
+        const float thr_f = row_ok ? (tk ? key_float(tk) : -INFINITY) : INFINITY;
+        const int cbase = n * kTcTileN + cpart * kTcColsPerPart;                // first column of this thread's slice
+        // seen items of the other column quarters of the previous / this tile are skipped, not patched
+        while (next_seen < cbase) {
+          ++s_cur;
+          next_seen = s_cur < s_end ? __ldg(p.seen_idx + s_cur) : 0x7fffffff;
+        }
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
-        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride;
-#pragma unroll 1
-        for (int cq = 0; cq < kTcTileN; cq += 64) {
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride + cpart * kTcColsPerPart;
 #pragma unroll
-          for (int c1 = 0; c1 < 64; c1 += 16) {
-            const int col0 = n * kTcTileN + cq + c1;
-            uint32_t r[16];
-            tmem_ld16(t_row + cq + c1, r);
-            float mv[16];
-            if (MUL) {
-              if (row_ok && col0 + 16 <= p.n_items && (p.ldmul & 3) == 0 && ((uintptr_t)p.mul & 15) == 0) {
+        for (int c1 = 0; c1 < kTcColsPerPart; c1 += 16) {
+          const int col0 = cbase + c1;
+          uint32_t r[16];
+          tmem_ld16(t_row + c1, r);
+          float mv[16];
+          if (MUL) {
+            if (row_ok && col0 + 16 <= p.n_items && (p.ldmul & 3) == 0 && ((uintptr_t)p.mul & 15) == 0) {
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                  const float4 m4 = __ldg(reinterpret_cast<const float4*>(mrow + col0 + j));
-                  mv[j] = m4.x; mv[j + 1] = m4.y; mv[j + 2] = m4.z; mv[j + 3] = m4.w;
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) mv[j] = (row_ok && col0 + j < p.n_items) ? __ldg(mrow + col0 + j) : 0.f;
+              for (int j = 0; j < 16; j += 4) {
+                const float4 m4 = __ldg(reinterpret_cast<const float4*>(mrow + col0 + j));
+                mv[j] = m4.x; mv[j + 1] = m4.y; mv[j + 2] = m4.z; mv[j + 3] = m4.w;
               }
-            }
-            tmem_ld_wait();
-            float out[16];
+            } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) out[j] = MUL ? __uint_as_float(r[j]) * mv[j] : __uint_as_float(r[j]);
-            // seen pairs inside these 16 columns (rare): fill value (x multiplier) or NaN = never selected
-            while (next_seen < col0 + 16) {
-              const int js = next_seen - col0;
-              float v = p.exclude_seen ? __int_as_float(0x7fc00000) : p.fill;
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (j == js) out[j] = (MUL && !p.exclude_seen) ? v * mv[j] : v;
-              ++s_cur;
-              next_seen = s_cur < s_end ? __ldg(p.seen_idx + s_cur) : 0x7fffffff;
-            }
-            if (row_ok) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                if (out[j] >= sel_thr_f && col0 + j < p.n_items) {
-                  const unsigned long long key = make_key(float_key(out[j]), (uint32_t)(col0 + j));
-                  if (key > sel_thr) sel_buf[sel_cnt++] = key;
-                }
-              }
+              for (int j = 0; j < 16; ++j) mv[j] = (row_ok && col0 + j < p.n_items) ? __ldg(mrow + col0 + j) : 0.f;
             }
           }
-          // overflow check every 64 columns: rows that could not take another 64 survivors are compacted by the warp
-          uint32_t need = __ballot_sync(0xffffffffu, sel_cnt + 64 > kCandCap);
-          while (need) {
-            const int rl = __ffs(need) - 1;
-            need &= need - 1u;
-            unsigned long long* b = reinterpret_cast<unsigned long long*>(
-                __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(sel_buf), rl));
-            const int c = __shfl_sync(0xffffffffu, sel_cnt, rl);
-            unsigned long long t;
-            const int kept = warp_select<kCandCap / 32>(b, c, p.k, lane, &t);
-            if (lane == rl) {
-              sel_cnt = kept;
-              sel_thr = t;
-              sel_thr_f = t ? key_float((uint32_t)(t >> 32)) : -INFINITY;
+          tmem_ld_wait();
+          float out[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) out[j] = MUL ? __uint_as_float(r[j]) * mv[j] : __uint_as_float(r[j]);
+          // seen pairs inside these 16 columns (rare): fill value (x multiplier) or NaN = never selected
+          while (next_seen < col0 + 16) {
+            const int js = next_seen - col0;
+            const float v = p.exclude_seen ? __int_as_float(0x7fc00000) : p.fill;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j == js) out[j] = (MUL && !p.exclude_seen) ? v * mv[j] : v;
+            ++s_cur;
+            next_seen = s_cur < s_end ? __ldg(p.seen_idx + s_cur) : 0x7fffffff;
+          }
+          // fast path: ONE compare per 16 scores (their maximum against the threshold; fmaxf ignores the NaN marks)
+          float mx = fmaxf(fmaxf(fmaxf(out[0], out[1]), fmaxf(out[2], out[3])), fmaxf(fmaxf(out[4], out[5]), fmaxf(out[6], out[7])));
+          mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(out[8], out[9]), fmaxf(out[10], out[11])),
+                               fmaxf(fmaxf(out[12], out[13]), fmaxf(out[14], out[15]))));
+          if (mx >= thr_f) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (out[j] >= thr_f && col0 + j < p.n_items) {
+                const unsigned long long key = make_key(float_key(out[j]), (uint32_t)(col0 + j));
+                if (key > sel_thr) sel_buf[sel_cnt++] = key;
+              }
             }
           }
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_leader(&tempty[acc]);
+        if (lane == 0) mbar_arrive_leader(&tempty[acc]);   // accumulator free: the next tile's MMAs may start
+        // a thread offers at most 64 scores per tile: rows that could not take another 64 survivors are compacted now,
+        // one row at a time, by the whole warp; the new k-th best is published for the row's other column quarters
+        uint32_t need = __ballot_sync(0xffffffffu, sel_cnt + kTcColsPerPart > kCandCap);
+        while (need) {
+          const int rl = __ffs(need) - 1;
+          need &= need - 1u;
+          unsigned long long* b = reinterpret_cast<unsigned long long*>(
+              __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(sel_buf), rl));
+          const int c = __shfl_sync(0xffffffffu, sel_cnt, rl);
+          unsigned long long t;
+          const int kept = warp_select<kCandCap / 32>(b, c, p.k, lane, &t);
+          if (lane == rl) {
+            sel_cnt = kept;
+            sel_thr = t;
+            if (t) atomicMax(&s_row_thr[rloc], (uint32_t)(t >> 32));
+          }
+        }
       }
-      if (row_ok) p.cand_cnt[(size_t)lrow * p.segs + seg] = sel_cnt;
+      if (row_ok) p.cand_cnt[(size_t)lrow * (p.segs * kTcColParts) + vseg] = sel_cnt;
     }
   }
 
@@ -354,7 +385,7 @@ static TcWs tc_layout(int64_t n_users_total, int64_t n_items, int64_t rows, int 
   size_t off = 0;
   w.xu = off; off += align_up((size_t)2 * n_users_total * dim * sizeof(float), 256);
   w.xi = off; off += align_up((size_t)2 * n_items * dim * sizeof(float), 256);
-  const size_t rs = (size_t)rows * tc_segments(rows, n_items);
+  const size_t rs = (size_t)rows * tc_segments(rows, n_items) * kTcColParts;
   w.cand = off; off += align_up(rs * kCandCap * sizeof(unsigned long long), 256);
   w.cnt = off; off += align_up(rs * sizeof(int), 256);
   w.total = off;
@@ -434,21 +465,21 @@ extern "C" int lgc_score_topk_tc(const float* Xu, const float* Xi, int64_t n_use
   const int grid = 2 * clusters;
 #define LGC_TC_LAUNCH(KBV, MULV)                                                                             \
   do {                                                                                                       \
-    constexpr size_t smem = (size_t)(2 * KBV + kTcStages * 2 * KBV) * kTcKbBytes + 1024 + 256;               \
+    constexpr size_t smem = (size_t)(2 * KBV + kTcStages * 2 * KBV) * kTcKbBytes + 1024 + 256 + 512;         \
     static DeviceOnce attr;                                                                                  \
     if (attr.need()) {                                                                                       \
       LGC_CUDA(cudaFuncSetAttribute(score_topk_tc_kernel<KBV, MULV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                     (int)smem));                                                             \
       attr.mark();                                                                                           \
     }                                                                                                        \
-    score_topk_tc_kernel<KBV, MULV><<<grid, kThreads, smem, stream>>>(tmU, tmI, p);                          \
+    score_topk_tc_kernel<KBV, MULV><<<grid, kTcThreads, smem, stream>>>(tmU, tmI, p);                        \
   } while (0)
   if (dim == 64) { if (mul) LGC_TC_LAUNCH(2, true); else LGC_TC_LAUNCH(2, false); }
   else { if (mul) LGC_TC_LAUNCH(1, true); else LGC_TC_LAUNCH(1, false); }
 #undef LGC_TC_LAUNCH
   LGC_LAUNCH_CHECK("score_topk_tc_kernel");
   topk_merge_kernel<kCandCap><<<(unsigned)ceil_div(rows, kMergeWarps), kMergeWarps * 32, 0, stream>>>(
-      p.cand, p.cand_cnt, rows, p.segs, k, out_idx, out_val);
+      p.cand, p.cand_cnt, rows, p.segs * kTcColParts, k, out_idx, out_val);
   LGC_LAUNCH_CHECK("topk_merge_kernel");
   return LGC_OK;
 }

@@ -599,7 +599,7 @@ class SpreadingEngine:
         deg = self.ki if diversity else None
         lambdas = [float(x) for x in lambdas]
         sums = torch.zeros((len(lambdas), 6), dtype=torch.float64, device=self.dev)
-        fuse = layer0 is None and gscore is None and self.can_fuse_topk(k, self.U)   # F never materialised
+        fuse = layer0 is None and gscore is None and self.prefer_fused_topk(k, self.U)   # F never materialised
         F = None if fuse else torch.empty((self.U, _pad(self.M, 4)), dtype=torch.float32, device=self.dev)[:, : self.M]
         for n, lam in enumerate(lambdas):
             if layer0 is not None:
@@ -663,7 +663,18 @@ class SpreadingEngine:
         return idx, val
 
     def can_fuse_topk(self, k: int, rows: int) -> bool:
-        return self.w_kind == 1 and k <= 32 and rows > 128 and os.environ.get("LGCNHS_NO_FUSED_TOPK", "0") != "1"
+        return self.w_kind == 1 and k <= 32 and rows > 128
+
+    def prefer_fused_topk(self, k: int, rows: int) -> bool:
+        """Default choice of recommend() / sweep().  The fused epilogue never writes F (14.8 GB at the ML-20M shape) but
+        its selection runs on the GEMM's four epilogue warps; it pays when F is large (the materialised path is then
+        bound by writing and re-reading F) and is requested explicitly (fused=True / LGCNHS_FUSED_TOPK=1) otherwise."""
+        if not self.can_fuse_topk(k, rows):
+            return False
+        env = os.environ.get("LGCNHS_FUSED_TOPK")
+        if env is not None:
+            return env == "1"
+        return rows * self.M * 4 > (2 << 30)
 
     def recommend(self, lam: float, k: int, filtered: bool = True, gscore: Optional[torch.Tensor] = None,
                   user_range: Optional[tuple[int, int]] = None, F_out: Optional[torch.Tensor] = None,
@@ -677,7 +688,7 @@ class SpreadingEngine:
         self.scale(lam)
         u0, u1 = (0, self.U) if user_range is None else user_range
         if fused is None:
-            fused = gscore is None and F_out is None and self.can_fuse_topk(k, u1 - u0)
+            fused = gscore is None and F_out is None and self.prefer_fused_topk(k, u1 - u0)
         if fused:
             if gscore is not None:
                 raise LgcnhsError("recommend: the fused epilogue has no Hadamard factor; pass fused=False")

@@ -283,6 +283,7 @@ def test_score_topk_tensor_core_seen_rule_and_ties(dev):
     iw[301] = iw[300]                                       # exact tie for every user
     dense_seen = torch.rand(U, M, generator=g) < 0.2
     dense_seen[:4, 5:] = True                               # four users have only items 0..4 unseen
+    dense_seen[:4, :5] = False
     su, si = torch.nonzero(dense_seen, as_tuple=True)
     seen = ops.seen_csr(su.to(dev), si.to(dev), U, M)
     idx, val = ops.score_topk(uw.to(dev), iw.to(dev), k, seen)
