@@ -521,23 +521,29 @@ def w_build_leg(d, dev, rank: int, world: int, steps: int = 3):
             "mass_check": {"sum_G": round(checksum, 3), "nnz_A": int(sel.size)}}
 
 
-def training_leg(dev, steps: int, warmup: int):
-    """BASELINE config 4: LightGCN 3-layer dim-64 BPR training step + full-rank eval, Amazon-Book shape."""
-    from lgcnhs_b200.trainer import FusedBPRTrainer
+def training_leg(dev, steps: int, warmup: int, rank: int = 0, world: int = 1):
+    """BASELINE config 4: LightGCN 3-layer dim-64 BPR training step + full-rank eval, Amazon-Book shape, on `world` GPUs:
+    the rows of A_hat are partitioned over the ranks for the forward and the gradient propagation (fused peer-store
+    exchange), Adam runs on the rows a rank owns and pushes them to every replica, the evaluation is sharded by user
+    block (FusedBPRTrainer(distributed=True), sharded_topk_layer0)."""
+    from lgcnhs_b200 import ops
+    from lgcnhs_b200.trainer import FusedBPRTrainer, sharded_topk_layer0
     from model.LightGCN.evaluation import _topk_layer0
     from model.LightGCN.model import LightGCN
 
-    d = load_shape("amazon-book")
+    dist_on = world > 1
+    barrier = (lambda: torch.distributed.barrier()) if dist_on else None
+    d = load_shape("amazon-book", rank, barrier)
     adj_np, (tr, va, te) = train_adj(d)
     adj = torch.from_numpy(adj_np).to(dev)
     torch.manual_seed(42)
     model = LightGCN(d.n_users, d.n_items, DIM, K_LAYERS).to(dev)
-    trainer = FusedBPRTrainer(model, adj, lr=1e-3, eps_reg=1e-6)
+    trainer = FusedBPRTrainer(model, adj, lr=1e-3, eps_reg=1e-6, distributed=dist_on)
     B = 1024
     from model.LightGCN.loss import sampleMiniBatch
 
     # one reference iteration (train.py:125-144): sample a mini-batch (device negative sampler), forward, BPR,
-    # backward, Adam.
+    # backward, Adam.  Every rank draws the same mini-batch (same seed).
     train_ei = torch.from_numpy(np.stack([d.users[tr], d.items[tr]])).to(dev)
     torch.manual_seed(42)
 
@@ -545,24 +551,67 @@ def training_leg(dev, steps: int, warmup: int):
         u, p, n = sampleMiniBatch(B, train_ei)
         return trainer.step(u, p, n)
 
+    def sync():
+        torch.cuda.synchronize()
+        if dist_on:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if not dist_on:
+            return x
+        t = torch.tensor([x], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
     for i in range(max(warmup, 3)):
         one_step()
-    torch.cuda.synchronize()
+    sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
         loss = one_step()
     e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
+    sync()
+    ms = max_over_ranks(e0.elapsed_time(e1) / steps)
+    parity = None
+    if dist_on:
+        # all replicas of the weight table must be bit-identical (every row is written by exactly one owner)
+        chk = trainer.X0.double().sum().reshape(1)
+        lo, hi = chk.clone(), chk.clone()
+        torch.distributed.all_reduce(lo, op=torch.distributed.ReduceOp.MIN)
+        torch.distributed.all_reduce(hi, op=torch.distributed.ReduceOp.MAX)
+        parity = {"weight_replicas_identical": bool(lo.item() == hi.item())}
     e_tr = torch.from_numpy(np.stack([d.users[tr], d.items[tr]]))
-    _topk_layer0(model, d.n_users, d.n_items, [e_tr], 20)
-    torch.cuda.synchronize()
-    e0.record()
-    _topk_layer0(model, d.n_users, d.n_items, [e_tr], 20)
-    e1.record()
-    torch.cuda.synchronize()
-    ms_eval = e0.elapsed_time(e1)
+    if dist_on:
+        seen = ops.seen_csr(e_tr[0].to(dev), e_tr[1].to(dev), d.n_users, d.n_items)
+        full, mine = sharded_topk_layer0(model, d.n_users, d.n_items, seen, 20, rank, world)
+        sync()
+        e0.record()
+        full, mine = sharded_topk_layer0(model, d.n_users, d.n_items, seen, 20, rank, world)
+        e1.record()
+        sync()
+        ms_eval = max_over_ranks(e0.elapsed_time(e1))
+        ref = _topk_layer0(model, d.n_users, d.n_items, [e_tr], 20)      # the same ranking on one GPU
+        parity["eval_lists_equal_1gpu"] = bool(torch.equal(ref, full))
+    else:
+        _topk_layer0(model, d.n_users, d.n_items, [e_tr], 20)
+        torch.cuda.synchronize()
+        e0.record()
+        _topk_layer0(model, d.n_users, d.n_items, [e_tr], 20)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_eval = e0.elapsed_time(e1)
+    if dist_on:
+        return {"workload": f"LightGCN K=3 D=64 BPR step (batch {B}) + full-rank top-20 eval, amazon-book shape "
+                            f"(U={d.n_users}, M={d.n_items}, nnz={adj_np.shape[1]}) on {world} GPUs",
+                "step_ms": round(ms, 4), "loss": round(float(loss[0]), 5), "scaling": "strong",
+                "eval_ms": round(ms_eval, 3), "eval_users_per_s": round(d.n_users / (ms_eval * 1e-3), 1),
+                "parity": parity,
+                "what": "rows of A_hat partitioned by nnz (users and items separately) for the forward and the gradient "
+                        "propagation with the fused peer-store exchange + device barrier per layer; BPR replicated (same "
+                        "batch); Adam on owned rows, new rows pushed to every replica over NVLink; eval sharded by user block, "
+                        "ids all-gathered; device time, max over ranks"}
     # e2e of the full-rank recommendation through the reference-facing call: recommendForAllUser(model, U, M, train_adj,
     # val_adj, test_adj, k) with the HOST adjacency tensors buildGraph returns -> dict{uid: [k ids]} (+ np.save)
     try:
@@ -832,6 +881,13 @@ def main():
             wb = {"error": repr(e)[:300]}
         if rank == 0:
             line["w_build"] = wb
+    if world > 1 and not args.no_spreading:
+        try:
+            tl = training_leg(dev, steps=max(5, min(args.steps, 20)), warmup=3, rank=rank, world=world)
+        except Exception as e:
+            tl = {"error": repr(e)[:300]}
+        if rank == 0:
+            line["training"] = tl
     if rank == 0 and world == 1 and not args.no_spreading:
         try:
             line["training"] = training_leg(dev, steps=max(5, min(args.steps, 20)), warmup=3)

@@ -221,6 +221,11 @@ int lgc_score_topk_tc(const float* Xu, const float* Xi, int64_t n_users_total, i
 int lgc_peer_barrier(const int32_t* local_flags, int32_t* const* peer_flags_host, int32_t my_rank,
                      int32_t n_peers, int32_t epoch, lgc_stream_t stream);
 
+/* Same barrier with the epoch counter in device memory (the kernel increments *epoch_counter_dev and uses the new
+ * value): capturable in a CUDA graph, replayable — all ranks must issue the same sequence of barriers. */
+int lgc_peer_barrier_dev(const int32_t* local_flags, int32_t* const* peer_flags_host, int32_t my_rank,
+                         int32_t n_peers, int32_t* epoch_counter_dev, lgc_stream_t stream);
+
 /* Tuning knob of lgc_score_topk: CTA size (256 or 512 threads) of the 128-user tile variant. */
 int lgc_score_topk_config(int32_t threads);
 
@@ -392,6 +397,20 @@ int lgc_spmm_layer_bcast(const int32_t* rowptr, const int32_t* colidx, const flo
                          const float* X0, float alpha, float beta,
                          float* const* peer_Y_host, int32_t n_peers, float* partial,
                          int32_t* counters, lgc_stream_t stream);
+
+/* Adam (torch.optim.Adam.step, model/LightGCN/train.py:104,144) on elements [offset, offset + n) of the parameter
+ * table with the step-dependent scalars in device memory (lgc_adam_hyper_step), the gradient given as grad + grad2
+ * (grad2 may be null: the propagated gradient and the sparse direct rows need no separate add pass), and the updated
+ * parameters stored into n_peers replicas of the table (peer_tables_host[r]: rank r's copy mapped through CUDA IPC;
+ * n_peers = 0: param_table only).  Multi-GPU (SURVEY 8e "gradient rows live where the shard lives"): the owner of a row
+ * range is the only rank that updates it and pushes the new rows to every replica over NVLink. */
+int lgc_adam_step_fused(float* param_table, float* const* peer_tables_host, int32_t n_peers, const float* grad,
+                        const float* grad2, float* exp_avg, float* exp_avg_sq, int64_t offset, int64_t n,
+                        float beta1, float beta2, float eps, const float* hyper_dev, lgc_stream_t stream);
+/* Zero the rows users[b], n_users + pos[b], n_users + neg[b] of up to two (N, dim) gradient tables (a, b; either may
+ * be null): the clean-up after a step, instead of a memset of the whole tables. */
+int lgc_zero_rows(float* a, float* b, int32_t dim, const int64_t* users, const int64_t* pos, const int64_t* neg,
+                  int64_t batch, int64_t n_users, lgc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Measurement probe (bench.py): uniformly random whole-row reads (dim fp32 per row, 128-bit

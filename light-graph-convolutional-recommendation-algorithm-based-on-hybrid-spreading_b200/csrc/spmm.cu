@@ -231,6 +231,36 @@ __global__ void peer_barrier_kernel(const int32_t* __restrict__ local_flags, Pee
   }
 }
 
+// Same barrier with the epoch kept in device memory (incremented by the kernel itself), so that a sequence of
+// propagation layers + barriers can be captured in a CUDA graph and replayed: every rank replays the same sequence, so
+// the epochs stay aligned without any host-side counter.
+__global__ void peer_barrier_dev_kernel(const int32_t* __restrict__ local_flags, PeerFlags peers, int my_rank, int n_peers,
+                                        int32_t* __restrict__ epoch_counter) {
+  __shared__ int32_t s_epoch;
+  if (threadIdx.x == 0) {
+    s_epoch = *epoch_counter + 1;
+    *epoch_counter = s_epoch;
+  }
+  __syncthreads();
+  const int32_t epoch = s_epoch;
+  const int p = threadIdx.x;
+  if (p < n_peers) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(peers.f[p] + my_rank), "r"(epoch) : "memory");
+    const long long t0 = clock64();
+    int32_t v;
+    do {
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(local_flags + p) : "memory");
+      if (v >= epoch) break;
+      if (clock64() - t0 > 20000000000ll) {
+        printf("lgcnhs peer barrier: rank %d never saw peer %d reach epoch %d\n", my_rank, p, epoch);
+        __trap();
+      }
+      __nanosleep(32);
+    } while (true);
+  }
+}
+
 template <int NPEER>
 static int launch_spmm(const int32_t* rowptr, const int32_t* colidx, const float* val,
                        const int32_t* chunk_row, const int32_t* chunk_start,
@@ -369,6 +399,20 @@ extern "C" int lgc_peer_barrier(const int32_t* local_flags, int32_t* const* peer
   }
   peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(local_flags, pf, my_rank, n_peers, epoch);
   LGC_LAUNCH_CHECK("peer_barrier_kernel");
+  return LGC_OK;
+}
+
+extern "C" int lgc_peer_barrier_dev(const int32_t* local_flags, int32_t* const* peer_flags_host, int32_t my_rank,
+                                    int32_t n_peers, int32_t* epoch_counter_dev, lgc_stream_t stream) {
+  LGC_REQUIRE(local_flags && peer_flags_host && epoch_counter_dev, "peer barrier: null pointer");
+  LGC_REQUIRE(n_peers >= 1 && n_peers <= kMaxPeers && my_rank >= 0 && my_rank < n_peers, "peer barrier: bad rank");
+  PeerFlags pf{};
+  for (int p = 0; p < n_peers; ++p) {
+    LGC_REQUIRE(peer_flags_host[p], "peer barrier: null peer flag array");
+    pf.f[p] = peer_flags_host[p];
+  }
+  peer_barrier_dev_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(local_flags, pf, my_rank, n_peers, epoch_counter_dev);
+  LGC_LAUNCH_CHECK("peer_barrier_dev_kernel");
   return LGC_OK;
 }
 

@@ -179,6 +179,57 @@ __global__ void adam_kernel(float4* __restrict__ p, const float4* __restrict__ g
   }
 }
 
+// Adam on a slice of the parameter table with (1) the gradient given as the sum of two buffers — the propagated
+// gradient and the sparse direct (regulariser) rows — so that no separate add pass is needed, and (2) the updated
+// parameters stored into every replica of the table (multi-GPU: peers[r] = rank r's copy of the table, mapped through
+// CUDA IPC; the owner of a row range is the only rank that updates it, and pushes the result over NVLink).
+struct ParamPeers {
+  float* p[8];
+};
+
+__global__ void adam_fused_kernel(const float4* __restrict__ p_local, ParamPeers peers, int n_peers,
+                                  const float4* __restrict__ g1, const float4* __restrict__ g2, float4* __restrict__ m,
+                                  float4* __restrict__ v, int64_t off4, int64_t n4, float beta1, float beta2, float eps,
+                                  const float* __restrict__ hyper) {
+  const float step_size = hyper[0], bc2_sqrt = hyper[1];
+  auto upd = [&](float& pp, float gg, float& mm, float& vv) {
+    mm = mm + (gg - mm) * (1.f - beta1);
+    vv = vv * beta2 + (1.f - beta2) * gg * gg;
+    const float denom = sqrtf(vv) / bc2_sqrt + eps;
+    pp = pp - step_size * (mm / denom);
+  };
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = off4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < off4 + n4; i += stride) {
+    float4 pp = p_local[i], gg = g1[i], mm = m[i], vv = v[i];
+    if (g2) {
+      const float4 h = g2[i];
+      gg.x += h.x; gg.y += h.y; gg.z += h.z; gg.w += h.w;
+    }
+    upd(pp.x, gg.x, mm.x, vv.x); upd(pp.y, gg.y, mm.y, vv.y);
+    upd(pp.z, gg.z, mm.z, vv.z); upd(pp.w, gg.w, mm.w, vv.w);
+    m[i] = mm; v[i] = vv;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (r < n_peers) reinterpret_cast<float4*>(peers.p[r])[i] = pp;
+  }
+}
+
+// zero the rows a mini-batch touched in up to two (N, dim) gradient buffers (instead of memset of the whole tables)
+__global__ void zero_rows_kernel(float* __restrict__ a, float* __restrict__ b, int dim, const int64_t* __restrict__ users,
+                                 const int64_t* __restrict__ pos, const int64_t* __restrict__ neg, int64_t batch,
+                                 int64_t n_users) {
+  const int lpr = dim / 4;
+  const int64_t t = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / lpr;
+  const int li = threadIdx.x % lpr;
+  if (t >= 3 * batch) return;
+  const int64_t bi = t / 3;
+  const int which = (int)(t % 3);
+  const int64_t row = which == 0 ? users[bi] : n_users + (which == 1 ? pos[bi] : neg[bi]);
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (a) *reinterpret_cast<float4*>(a + row * dim + li * 4) = z;
+  if (b) *reinterpret_cast<float4*>(b + row * dim + li * 4) = z;
+}
+
 // ++step; hyper = {lr / (1 - beta1^step), sqrt(1 - beta2^step)}  — torch.optim.Adam's bias corrections
 // (float64 like the Python side of torch's single-tensor path, rounded once to fp32)
 __global__ void adam_hyper_kernel(long long* __restrict__ step, const float* __restrict__ lr, double beta1, double beta2,
@@ -274,5 +325,46 @@ extern "C" int lgc_adam_step_dev(float* param, const float* grad, float* exp_avg
       (float4*)param, (const float4*)grad, (float4*)exp_avg, (float4*)exp_avg_sq, n4, param + n4 * 4,
       grad + n4 * 4, exp_avg + n4 * 4, exp_avg_sq + n4 * 4, tail, beta1, beta2, eps, 0.f, 1.f, hyper_dev);
   LGC_LAUNCH_CHECK("adam_kernel");
+  return LGC_OK;
+}
+
+extern "C" int lgc_adam_step_fused(float* param_table, float* const* peer_tables_host, int32_t n_peers, const float* grad,
+                                   const float* grad2, float* exp_avg, float* exp_avg_sq, int64_t offset, int64_t n,
+                                   float beta1, float beta2, float eps, const float* hyper_dev, lgc_stream_t stream) {
+  LGC_REQUIRE(param_table && grad && exp_avg && exp_avg_sq && hyper_dev && n > 0 && offset >= 0, "adam fused: null pointer / empty");
+  LGC_REQUIRE((((uintptr_t)param_table | (uintptr_t)grad | (uintptr_t)grad2 | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0,
+              "adam fused: buffers must be 16-byte aligned");
+  LGC_REQUIRE((offset & 3) == 0 && (n & 3) == 0, "adam fused: offset and count must be multiples of 4 elements");
+  LGC_REQUIRE(n_peers >= 0 && n_peers <= 8 && (n_peers == 0 || peer_tables_host), "adam fused: 0..8 replicas");
+  ParamPeers peers{};
+  int np = n_peers;
+  if (np == 0) {
+    peers.p[0] = param_table;
+    np = 1;
+  } else {
+    for (int r = 0; r < n_peers; ++r) {
+      LGC_REQUIRE(peer_tables_host[r] && ((uintptr_t)peer_tables_host[r] & 15) == 0, "adam fused: bad replica pointer");
+      peers.p[r] = peer_tables_host[r];
+    }
+  }
+  const int64_t n4 = n / 4;
+  int64_t grid = ceil_div(n4, 256);
+  const int64_t cap = (int64_t)num_sms() * 16;
+  if (grid > cap) grid = cap;
+  adam_fused_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+      (const float4*)param_table, peers, np, (const float4*)grad, (const float4*)grad2, (float4*)exp_avg, (float4*)exp_avg_sq,
+      offset / 4, n4, beta1, beta2, eps, hyper_dev);
+  LGC_LAUNCH_CHECK("adam_fused_kernel");
+  return LGC_OK;
+}
+
+extern "C" int lgc_zero_rows(float* a, float* b, int32_t dim, const int64_t* users, const int64_t* pos, const int64_t* neg,
+                             int64_t batch, int64_t n_users, lgc_stream_t stream) {
+  LGC_REQUIRE((a || b) && users && pos && neg && batch > 0, "zero_rows: null pointer / empty batch");
+  LGC_REQUIRE(dim == 32 || dim == 64 || dim == 128, "zero_rows: dim must be 32, 64 or 128");
+  LGC_REQUIRE((((uintptr_t)a | (uintptr_t)b) & 15) == 0, "zero_rows: buffers must be 16-byte aligned");
+  const int64_t threads = 3 * batch * (dim / 4);
+  zero_rows_kernel<<<(unsigned)ceil_div(threads, 256), 256, 0, (cudaStream_t)stream>>>(a, b, dim, users, pos, neg, batch, n_users);
+  LGC_LAUNCH_CHECK("zero_rows_kernel");
   return LGC_OK;
 }

@@ -43,14 +43,34 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must trap (sticky CUDA error) instead of hanging the GPU.
+// try_wait with a suspend-time hint: the thread is parked by the hardware (it does not occupy issue slots of its
+// scheduler, which the epilogue warps of the same SM sub-partition need) until the phase completes or ~hint_ns pass
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must trap (sticky CUDA error) instead of hanging the GPU.  The clock is only read every
+// 256 unsuccessful (parked) tries: the spin loops of the producer / MMA / waiting epilogue warps were 23 % of all
+// issued instructions of the fused score kernel (ncu, profiles/r2_ncu_score_tc.txt).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) {  // ~2 s at 2 GHz
-      printf("lgcnhs umma_gemm: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
+  long long t0 = 0;
+  for (uint32_t spins = 1;; ++spins) {
+    if (mbar_try_wait_hint(bar, parity, 20000u)) return;
+    if ((spins & 255u) == 0u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 8000000000ll) {  // ~4 s at 2 GHz
+        printf("lgcnhs umma: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+        __trap();
+      }
     }
   }
 }

@@ -115,6 +115,8 @@ class RowPartitionedPropagation:
         if mode in ("p2p", "p2p-nccl"):
             # epoch flags live in their own allocation (cudaIpc handles cover whole allocations)
             self.flags = torch.zeros(64, dtype=torch.int32, device=self.dev)
+            # barrier epoch, incremented by the barrier kernel itself: the sequence can be captured in a CUDA graph
+            self.epoch_dev = torch.zeros(1, dtype=torch.int32, device=self.dev)
             blobs = [_ipc_export(b) for b in self.bufs] + [_ipc_export(self.flags)]
             gathered: list = [None] * self.world
             dist.all_gather_object(gathered, blobs)
@@ -128,15 +130,23 @@ class RowPartitionedPropagation:
         torch.cuda.synchronize()
         dist.barrier()
 
+    def peer_barrier(self):
+        """Stream-ordered device barrier over all ranks (epoch flags in peer memory): returns on this rank's stream
+        once every rank's preceding work on ITS stream (row stores into our replicas included) has completed."""
+        farr = (C.c_void_p * self.world)(*[C.c_void_p(p) for p in self.peer_flag_ptrs])
+        check(lib().lgc_peer_barrier_dev(self.flags.data_ptr(), farr, self.rank, self.world, self.epoch_dev.data_ptr(),
+                                         torch.cuda.current_stream().cuda_stream), "peer barrier")
+
     def _layer_barrier(self):
         # stream-ordered: completes only after every rank's SpMM (and its peer stores) has finished
         dist.all_reduce(self._flag)
 
-    def propagate_mean(self, x0: torch.Tensor, layers: int) -> torch.Tensor:
-        """x0 is replicated on every rank; returns the replicated E = mean_l A_hat^l x0."""
+    def propagate_mean(self, x0: torch.Tensor, layers: int, result: Optional[int] = None) -> torch.Tensor:
+        """x0 is replicated on every rank; returns the replicated E = mean_l A_hat^l x0.
+        result: which of the two result buffers (0 / 1) receives it; default alternates between calls."""
         g = self.g
         cur = x0
-        res = 2 + (self._calls & 1)
+        res = 2 + ((self._calls & 1) if result is None else int(result))
         self._calls += 1
         for l in range(layers):
             last = l == layers - 1
@@ -145,10 +155,7 @@ class RowPartitionedPropagation:
             if self.mode == "p2p":
                 for a, b, ch in self.my_parts:
                     g.spmm_bcast(cur, x0, alpha, 1.0, self.peer_ptrs[oi], a, b, ch)
-                self.epoch += 1
-                farr = (C.c_void_p * self.world)(*[C.c_void_p(p) for p in self.peer_flag_ptrs])
-                check(lib().lgc_peer_barrier(self.flags.data_ptr(), farr, self.rank, self.world, self.epoch,
-                                             torch.cuda.current_stream().cuda_stream), "peer barrier")
+                self.peer_barrier()
             elif self.mode == "p2p-nccl":
                 for a, b, ch in self.my_parts:
                     g.spmm_bcast(cur, x0, alpha, 1.0, self.peer_ptrs[oi], a, b, ch)

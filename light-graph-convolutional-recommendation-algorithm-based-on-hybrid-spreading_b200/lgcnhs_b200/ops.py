@@ -256,14 +256,15 @@ def _bpr_scr(dev: torch.device) -> torch.Tensor:
 
 def bpr_fwd_bwd(E: torch.Tensor, X0: torch.Tensor, n_users: int, n_items: int, users: torch.Tensor,
                 pos: torch.Tensor, neg: torch.Tensor, eps: float, gE: Optional[torch.Tensor] = None,
-                gX0: Optional[torch.Tensor] = None, grad_scale: float = 1.0) -> torch.Tensor:
+                gX0: Optional[torch.Tensor] = None, grad_scale: float = 1.0,
+                loss_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Returns loss_out = [total, bpr]; if gE/gX0 are given the row gradients are scatter-added."""
     E = _req(E, torch.float32, "E")
     X0 = _req(X0, torch.float32, "X0")
     dim = int(E.shape[1])
     for t, nm in ((users, "users"), (pos, "pos"), (neg, "neg")):
         _req(t, torch.int64, nm)
-    loss = torch.empty(2, dtype=torch.float32, device=E.device)
+    loss = torch.empty(2, dtype=torch.float32, device=E.device) if loss_out is None else loss_out
     check(lib().lgc_bpr_fwd_bwd(_ptr(E), _ptr(X0), n_users, n_items, dim, _ptr(users), _ptr(pos), _ptr(neg),
                                 int(users.numel()), float(eps), float(grad_scale), _ptr(loss), _ptr(gE), _ptr(gX0),
                                 _ptr(_bpr_scr(E.device)), _stream()), "bpr")

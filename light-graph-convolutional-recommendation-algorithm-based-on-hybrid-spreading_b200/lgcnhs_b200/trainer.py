@@ -9,6 +9,7 @@ scatter, K fused SpMM launches on the gradient, two Adam kernels; no host sync i
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
 import os
 from typing import Optional
@@ -16,41 +17,86 @@ from typing import Optional
 import torch
 
 from . import ops
+from ._lib import check, lib
 from .propagation import graphs_for
 
 
 class FusedBPRTrainer:
-    """graph=True (default) captures the whole step — 2K SpMM layers, BPR, gradient merge, Adam — in ONE CUDA graph
-    after two eager warm-up steps: the step is launch-bound on small graphs (ML-100K: ~14 launches of a few
-    microseconds each), and every step-dependent scalar (Adam's bias corrections, the learning rate) lives in
-    device memory so that the captured graph stays valid.  Set LGCNHS_NO_GRAPH=1 to force eager launches."""
+    """One reference training iteration as a handful of fused kernels; graph=True (default) captures the whole step —
+    2K SpMM layers, BPR, Adam, clean-up — in ONE CUDA graph after two eager warm-up steps: the step is launch-bound on
+    small graphs (ML-100K: ~14 launches of a few microseconds each), and every step-dependent scalar (Adam's bias
+    corrections, the learning rate) lives in device memory so that the captured graph stays valid.
+    LGCNHS_NO_GRAPH=1 forces eager launches.
+
+    Memory traffic of a step beyond the 2K SpMM layers (round 2): the model's two weight tensors are VIEWS of one
+    (U+M, D) table, so the forward needs no gather of e^0; the gradient tables are cleaned by zeroing only the rows the
+    batch touched (lgc_zero_rows) instead of two full memsets; Adam reads the propagated gradient and the sparse direct
+    rows as two operands (lgc_adam_step_fused) instead of a separate add pass.
+
+    distributed=True (BASELINE config 4 at 2/4/8 GPUs; needs an initialised NCCL process group, one
+    process per GPU): the rows of A_hat are partitioned over the ranks for BOTH propagations (forward and gradient,
+    RowPartitionedPropagation: fused SpMM + peer-store all-gather + device barrier, no NCCL call in the step); every
+    rank evaluates the (tiny) BPR kernel on the same mini-batch; Adam runs only on the rows a rank owns and stores the
+    updated rows into every rank's weight table over NVLink, followed by one device barrier.  The loss is replicated
+    (no reduction needed).  All ranks must draw the same mini-batches (same torch seed)."""
 
     def __init__(self, model, train_adj_index: torch.Tensor, lr: float, eps_reg: float,
-                 betas=(0.9, 0.999), adam_eps: float = 1e-8, graph: Optional[bool] = None):
+                 betas=(0.9, 0.999), adam_eps: float = 1e-8, graph: Optional[bool] = None, distributed: bool = False):
         self.model = model
         self.U, self.M = model.user_num, model.item_num
         self.N, self.D, self.K = self.U + self.M, model.embedding_dim, model.layers
-        self.uw, self.iw = model.users_emb.weight, model.items_emb.weight
-        if not self.uw.is_cuda:
+        if not model.users_emb.weight.is_cuda:
             raise RuntimeError("FusedBPRTrainer: the model must live on a CUDA device (no CPU fallback)")
         if self.D not in (32, 64):
             # fail before the first step, not at the first evaluation: the SpMM / BPR / Adam kernels also take 128,
-            # the full-rank evaluation kernel (lgc_score_topk) takes 32 and 64
+            # the full-rank evaluation kernels (lgc_score_topk, lgc_score_topk_tc) take 32 and 64
             raise RuntimeError(f"FusedBPRTrainer: embedding_dim {self.D} not supported (32 or 64)")
-        dev = self.uw.device
+        dev = model.users_emb.weight.device
         self.dev = dev
-        self.g, self.gt = graphs_for(train_adj_index, self.N)
+        self.distributed = bool(distributed)
         z = lambda: torch.zeros((self.N, self.D), dtype=torch.float32, device=dev)  # noqa: E731
-        self.X0, self.E, self.gE, self.gX, self.tmp0, self.tmp1, self.gP = z(), z(), z(), z(), z(), z(), z()
+        # one weight table; the module's parameters become views of it (same Parameter objects, same values)
+        self.X0 = z()
+        with torch.no_grad():
+            self.X0[: self.U].copy_(model.users_emb.weight)
+            self.X0[self.U:].copy_(model.items_emb.weight)
+            model.users_emb.weight.data = self.X0[: self.U]
+            model.items_emb.weight.data = self.X0[self.U:]
+        self.uw, self.iw = model.users_emb.weight, model.items_emb.weight
+        self.gE, self.gX = z(), z()
         self.exp_avg, self.exp_avg_sq = z(), z()
         self.lr, self.eps_reg, self.betas, self.adam_eps = lr, eps_reg, betas, adam_eps
         self.t = 0
+        self.debug_keep_grad = False
+        self.grad_total: Optional[torch.Tensor] = None
         self.last_loss: Optional[torch.Tensor] = None
         # device-resident step state (graph mode)
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
         self.hyper_dev = torch.zeros(2, dtype=torch.float32, device=dev)
         self.loss_dev = torch.zeros(2, dtype=torch.float32, device=dev)
+        if self.distributed:
+            import torch.distributed as dist
+
+            from .dist import RowPartitionedPropagation, _ipc_export, _ipc_import
+
+            if not dist.is_initialized():
+                raise RuntimeError("FusedBPRTrainer(distributed=True) needs an initialised process group")
+            self.prop = RowPartitionedPropagation(train_adj_index, self.N, self.D, mode="p2p", split=self.U)
+            if not torch.equal(self.prop.g.rowptr, self.prop.g.transposed().rowptr):
+                raise RuntimeError("distributed training needs the symmetric bipartite adjacency")
+            self.rank, self.world = self.prop.rank, self.prop.world
+            blobs: list = [None] * self.world
+            dist.all_gather_object(blobs, _ipc_export(self.X0))
+            self.peer_tables = [self.X0.data_ptr() if r == self.rank else _ipc_import(blobs[r]) for r in range(self.world)]
+            self.own_rows = [(a, b) for a, b in self.prop.parts[self.rank] if b > a]
+            self.g = self.gt = self.prop.g
+            self.E = self.gP = None
+            torch.cuda.synchronize()
+            dist.barrier()
+        else:
+            self.g, self.gt = graphs_for(train_adj_index, self.N)
+            self.E, self.gP, self.tmp0, self.tmp1 = z(), z(), z(), z()
         if graph is None:
             graph = os.environ.get("LGCNHS_NO_GRAPH", "0") != "1"
         self.use_graph = bool(graph)
@@ -59,28 +105,47 @@ class FusedBPRTrainer:
         self._eager_steps = 0
 
     def forward_embeddings(self) -> tuple:
-        U = self.U
-        self.X0[:U].copy_(self.uw.detach())
-        self.X0[U:].copy_(self.iw.detach())
-        self.g.propagate_mean(self.X0, self.K, out=self.E, tmp=(self.tmp0, self.tmp1))
+        if self.distributed:
+            self.E = self.prop.propagate_mean(self.X0, self.K, result=0)
+        else:
+            self.g.propagate_mean(self.X0, self.K, out=self.E, tmp=(self.tmp0, self.tmp1))
         return self.X0, self.E
 
+    def _adam(self, a: int, b: int, grad: torch.Tensor) -> None:
+        """rows [a, b) of the weight table: g = grad + gX (direct rows), Adam, result into every replica."""
+        D = self.D
+        if self.distributed:
+            arr = (C.c_void_p * self.world)(*[C.c_void_p(p) for p in self.peer_tables])
+            n_peers = self.world
+        else:
+            arr, n_peers = None, 0
+        check(lib().lgc_adam_step_fused(self.X0.data_ptr(), arr, n_peers, grad.data_ptr(), self.gX.data_ptr(),
+                                        self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), a * D, (b - a) * D,
+                                        float(self.betas[0]), float(self.betas[1]), float(self.adam_eps),
+                                        self.hyper_dev.data_ptr(), torch.cuda.current_stream().cuda_stream), "adam fused")
+
     def _body(self, users: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor) -> None:
-        """Everything of one step that touches the device; identical in eager and captured form."""
+        """Everything of one step that touches the device; identical in eager and captured form.  gE / gX are all-zero
+        on entry and on exit."""
         X0, E = self.forward_embeddings()
-        self.gE.zero_()
-        self.gX.zero_()
-        loss = ops.bpr_fwd_bwd(E, X0, self.U, self.M, users, pos, neg, self.eps_reg, self.gE, self.gX)
-        self.loss_dev.copy_(loss)
+        ops.bpr_fwd_bwd(E, X0, self.U, self.M, users, pos, neg, self.eps_reg, self.gE, self.gX, loss_out=self.loss_dev)
         # dL/dX0 = mean_l (A^T)^l dL/dE  +  regulariser rows
-        self.gt.propagate_mean(self.gE, self.K, out=self.gP, tmp=(self.tmp0, self.tmp1))
-        self.gX.add_(self.gP)
-        U = self.U
+        if self.distributed:
+            gP = self.prop.propagate_mean(self.gE, self.K, result=1)
+        else:
+            gP = self.gt.propagate_mean(self.gE, self.K, out=self.gP, tmp=(self.tmp0, self.tmp1))
+        if self.debug_keep_grad:            # tests only (eager steps): the dense dL/dX0 that Adam consumes as two operands
+            self.grad_total = gP + self.gX
         ops.adam_hyper_step(self.step_dev, self.lr_dev, self.betas[0], self.betas[1], self.hyper_dev)
-        ops.adam_step_dev(self.uw.data, self.gX[:U], self.exp_avg[:U], self.exp_avg_sq[:U], self.betas[0], self.betas[1],
-                          self.adam_eps, self.hyper_dev)
-        ops.adam_step_dev(self.iw.data, self.gX[U:], self.exp_avg[U:], self.exp_avg_sq[U:], self.betas[0], self.betas[1],
-                          self.adam_eps, self.hyper_dev)
+        if self.distributed:
+            for a, b in self.own_rows:
+                self._adam(a, b, gP)
+            self.prop.peer_barrier()        # every rank's new rows are in every replica before the next forward
+        else:
+            self._adam(0, self.N, gP)
+        check(lib().lgc_zero_rows(self.gE.data_ptr(), self.gX.data_ptr(), self.D, users.data_ptr(), pos.data_ptr(),
+                                  neg.data_ptr(), int(users.numel()), self.U, torch.cuda.current_stream().cuda_stream),
+              "zero rows")
 
     def _capture(self, batch: int) -> None:
         dev = self.dev
@@ -118,6 +183,25 @@ class FusedBPRTrainer:
     # compulsory bytes of one step: every operand moved once (the row gathers of the SpMM are L2-served re-reads)
     def step_bytes_compulsory(self, batch: int) -> int:
         return 2 * self.K * self.g.layer_bytes_compulsory(self.D) + batch * 12 * 4 * self.D + 7 * self.N * 4 * self.D
+
+
+def sharded_topk_layer0(model, user_num: int, item_num: int, seen: tuple, k: int, rank: int, world: int):
+    """Full-rank evaluation sharded by USER BLOCK (SURVEY.md 8e "scoring + top-k: independent units"): rank r ranks users
+    [U r / P, U (r+1) / P) with the fused score/top-k kernel; the only exchange is the gather of the (U, k) ids."""
+    import torch.distributed as dist
+
+    xu = model.users_emb.weight.detach().contiguous()
+    xi = model.items_emb.weight.detach().contiguous()
+    u0, u1 = user_num * rank // world, user_num * (rank + 1) // world
+    idx, _ = ops.score_topk(xu, xi, k, seen, fill=-float(1 << 10), u0=u0, u1=u1, want_values=False)
+    blk = (user_num + world - 1) // world
+    pad = torch.full((blk, k), -1, dtype=torch.int64, device=xu.device)
+    pad[: u1 - u0] = idx
+    out = torch.empty((world * blk, k), dtype=torch.int64, device=xu.device)
+    dist.all_gather_into_tensor(out, pad)
+    rows = torch.cat([torch.arange(user_num * r // world, user_num * (r + 1) // world, device=xu.device) - user_num * r // world
+                      + r * blk for r in range(world)])
+    return out[rows], idx
 
 
 def choose_device() -> torch.device:

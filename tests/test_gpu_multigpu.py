@@ -40,3 +40,11 @@ def test_sharded_spreading_equals_single_gpu(world):
         pytest.skip(f"needs {world} GPUs")
     r = _torchrun(world, "check_multigpu_spread.py", "ml-1m")
     assert r.returncode == 0 and "MULTIGPU_SPREAD_OK" in r.stdout, (r.stdout[-3000:], r.stderr[-3000:])
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_distributed_training_step_equals_single_gpu(world):
+    if world not in _worlds():
+        pytest.skip(f"needs {world} GPUs")
+    r = _torchrun(world, "check_multigpu_train.py", "ml-100k")
+    assert r.returncode == 0 and "MULTIGPU_TRAIN_OK" in r.stdout, (r.stdout[-3000:], r.stderr[-3000:])

@@ -8,7 +8,7 @@ import numpy as np, torch  # noqa: E402
 from lgcnhs_b200 import ops  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--what", default="prop", choices=["prop", "spread", "both", "eval", "all"])
+ap.add_argument("--what", default="prop", choices=["prop", "spread", "both", "eval", "fusedtopk", "all"])
 ap.add_argument("--shape", default="ml-20m")
 ap.add_argument("--steps", type=int, default=2)
 a = ap.parse_args()
@@ -45,3 +45,14 @@ if a.what in ("eval", "all"):
         idx, _ = ops.score_topk(xu, xi, 20, seen, want_values=False)
     torch.cuda.synchronize()
     print("eval ok", int(idx.sum()))
+if a.what in ("fusedtopk", "all"):
+    # hs_resource_topk: top-20 selected inside the F-GEMM epilogue (ml-1m shape), and the symmetric G schedule
+    d = bench.load_shape("ml-1m")
+    tr, va, _ = d.split()
+    sel = np.concatenate([tr, va])
+    eng = ops.SpreadingEngine(d.n_users, d.n_items, torch.from_numpy(d.users[sel]).to(dev), torch.from_numpy(d.items[sel]).to(dev))
+    eng.general_w()
+    for lam in (0.3, 0.6):
+        idx, val = eng.recommend(lam, 20, fused=True)
+    torch.cuda.synchronize()
+    print("fusedtopk ok", int(idx.sum()))
