@@ -66,3 +66,55 @@ def lightgcn_forward(users_w: torch.Tensor, items_w: torch.Tensor, edge_index: t
     emb_final = PropagateMean.apply(emb_0, g, gt, layers)
     users_final, items_final = torch.split(emb_final, [n_users, n_items])
     return users_final, users_w, items_final, items_w
+
+
+class PipelinedPropagation:
+    """K-layer propagation of HOST embedding tables with the three legs of a call on three CUDA streams:
+
+        upload e^0 (pinned host -> device)  |  K fused SpMM layers + layer mean  |  download E (device -> pinned host)
+
+    A call returns as soon as its three legs are enqueued; consecutive calls overlap (the upload of call i+1 and the
+    download of call i-1 run while call i computes), so the sustained rate is set by the slowest leg instead of their
+    sum.  Two device buffer sets alternate between calls.  `synchronize()` waits for everything in flight; the result of
+    call i is valid in its `out_host` after `synchronize()` or after the event `submit` returns has completed.
+
+    This is the serving-style entry point behind LightGCN.forward for callers whose embeddings live on the host
+    (model/LightGCN/model.py:40-74 computes the same E; the reference moves the whole module to the device instead)."""
+
+    def __init__(self, edge_index: torch.Tensor, n_nodes: int, dim: int, layers: int, depth: int = 2):
+        if not edge_index.is_cuda:
+            raise RuntimeError("PipelinedPropagation: edge_index must be a CUDA tensor (no CPU fallback)")
+        self.g, _ = graphs_for(edge_index, n_nodes)
+        self.layers = layers
+        dev = edge_index.device
+        z = lambda: torch.empty((n_nodes, dim), dtype=torch.float32, device=dev)  # noqa: E731
+        self.slots = [{"x0": z(), "e": z(), "tmp": (z(), z()), "up": torch.cuda.Event(), "done": torch.cuda.Event(),
+                       "down": torch.cuda.Event()} for _ in range(depth)]
+        self.s_up, self.s_cmp, self.s_down = (torch.cuda.Stream(device=dev) for _ in range(3))
+        self.calls = 0
+
+    def submit(self, x0_host: torch.Tensor, out_host: torch.Tensor) -> torch.cuda.Event:
+        """Enqueue upload -> propagate -> download for one (n_nodes, dim) pinned host table; returns the event that
+        completes when `out_host` holds E."""
+        if not (x0_host.is_pinned() and out_host.is_pinned()):
+            raise RuntimeError("PipelinedPropagation: host tables must be pinned (torch.Tensor.pin_memory())")
+        sl = self.slots[self.calls % len(self.slots)]
+        self.calls += 1
+        with torch.cuda.stream(self.s_up):
+            self.s_up.wait_event(sl["done"])          # the previous propagation that read this slot's x0 has finished
+            sl["x0"].copy_(x0_host, non_blocking=True)
+            sl["up"].record(self.s_up)
+        with torch.cuda.stream(self.s_cmp):
+            self.s_cmp.wait_event(sl["up"])
+            self.s_cmp.wait_event(sl["down"])         # the previous download of this slot's E has finished
+            self.g.propagate_mean(sl["x0"], self.layers, out=sl["e"], tmp=sl["tmp"])
+            sl["done"].record(self.s_cmp)
+        with torch.cuda.stream(self.s_down):
+            self.s_down.wait_event(sl["done"])
+            out_host.copy_(sl["e"], non_blocking=True)
+            sl["down"].record(self.s_down)
+        return sl["down"]
+
+    def synchronize(self) -> None:
+        for s in (self.s_up, self.s_cmp, self.s_down):
+            s.synchronize()

@@ -157,3 +157,26 @@ def test_backward_on_non_symmetric_graph_matches_autograd(dev):
     (out * w.to(dev)).sum().backward()
     absA = sum(O.propagate_layers(w.abs(), torch.stack([ei[1], ei[0]]), 3)) / 4
     assert_close(xd.grad, xr.grad, "dX0 on a directed graph", sum_abs=absA + 1e-6)
+
+
+def test_pipelined_host_table_propagation(dev):
+    """PipelinedPropagation: upload / K layers / download on three streams with two buffer sets — every call must return
+    exactly what a plain propagate_mean of ITS input gives, also when calls with different inputs are in flight."""
+    from lgcnhs_b200.ops import NormGraph
+    from lgcnhs_b200.propagation import PipelinedPropagation
+
+    d, adj = make_graph("ml-100k")
+    n = d.n_users + d.n_items
+    adj = adj.to(dev)
+    g = NormGraph(adj, n)
+    pipe = PipelinedPropagation(adj, n, 64, 3)
+    gen = torch.Generator().manual_seed(1)
+    ins = [torch.randn(n, 64, generator=gen).pin_memory() for _ in range(5)]
+    outs = [torch.empty(n, 64).pin_memory() for _ in range(5)]
+    for x, o in zip(ins, outs):
+        pipe.submit(x, o)
+    pipe.synchronize()
+    for x, o in zip(ins, outs):
+        assert torch.equal(o, g.propagate_mean(x.to(dev), 3).cpu())
+    with pytest.raises(RuntimeError):
+        pipe.submit(torch.randn(n, 64), outs[0])          # unpinned host memory is refused
