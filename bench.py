@@ -488,14 +488,17 @@ def w_build_leg(d, dev, rank: int, world: int, steps: int = 3):
     U, M = d.n_users, d.n_items
     j0, j1 = M * rank // world, M * (rank + 1) // world
     operands = eng.pack_g_operands()
-    Gb = eng.general_w(item_range=(j0, j1), operands=operands)
+    # one GPU: the full matrix with the symmetric schedule (only the tiles touching the upper triangle are computed);
+    # N GPUs: rank r computes every tile of its column block (no exchange of mirrored tiles)
+    rng = None if world == 1 else (j0, j1)
+    Gb = eng.general_w(item_range=rng, operands=operands)
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        eng.general_w(item_range=(j0, j1), operands=operands, out=Gb)
+        eng.general_w(item_range=rng, operands=operands, out=Gb)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
@@ -513,11 +516,13 @@ def w_build_leg(d, dev, rank: int, world: int, steps: int = 3):
     tf = flops / (ms * 1e-3) / 1e12
     del operands, Gb, eng
     torch.cuda.empty_cache()
-    return {"workload": f"G = A^T K_u^-1 A on the ml-20m shape ({U}x{M}, nnz(A)={sel.size}), item-column blocks over {world} GPU(s), "
-                        "no data-path collective",
+    return {"workload": f"G = A^T K_u^-1 A on the ml-20m shape ({U}x{M}, nnz(A)={sel.size}), "
+                        + ("symmetric tile schedule on 1 GPU" if world == 1 else
+                           f"item-column blocks over {world} GPUs, no data-path collective"),
             "ms": round(ms, 3), "tflops": round(tf, 1), "scaling": "strong",
             "frac_of_bf16_peak": round(tf / (world * peak_sus), 4),
-            "peak_note": f"useful 2*M^2*U flops (4 int8 digit planes issued = 2 bf16-pass equivalents) / ({world} x {how} sustained bf16 peak)",
+            "peak_note": f"useful 2*M^2*U flops of the FULL matrix (SURVEY 8d counts one pass and the full, not the symmetric-half, G; "
+                         f"4 int8 digit planes = 2 bf16-pass equivalents are issued per computed tile) / ({world} x {how} sustained bf16 peak)",
             "mass_check": {"sum_G": round(checksum, 3), "nnz_A": int(sel.size)}}
 
 

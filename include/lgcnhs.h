@@ -221,6 +221,19 @@ int lgc_score_topk_tc(const float* Xu, const float* Xi, int64_t n_users_total, i
 int lgc_peer_barrier(const int32_t* local_flags, int32_t* const* peer_flags_host, int32_t my_rank,
                      int32_t n_peers, int32_t epoch, lgc_stream_t stream);
 
+/* Small graphs: all K layers + the layer mean of lgc_propagate_mean in ONE cooperative launch (layers separated by grid
+ * barriers instead of kernel launches; model/LightGCN/model.py:56-69 at the ML-100K / Douban shapes, where a layer is
+ * launch-latency bound).  Work units of <= 128 non-zeros: unit u covers non-zeros [unit_start[u], unit_end[u]) of row
+ * unit_row[u]; unit_slot[u] = -1 for a whole row, else the partial-sum slot of a piece of a long row; split_* list the
+ * long rows with their first slot and number of pieces (combined in order: deterministic).  partial: n_partials * dim
+ * floats.  Same result as lgc_propagate_mean up to fp32 summation order. */
+int lgc_propagate_mean_coop(const int32_t* rowptr, const int32_t* colidx, const float* val,
+                            const int32_t* unit_row, const int32_t* unit_start, const int32_t* unit_end,
+                            const int32_t* unit_slot, int32_t n_units, const int32_t* split_row,
+                            const int32_t* split_first, const int32_t* split_count, int32_t n_split,
+                            int64_t n_nodes, int32_t dim, int32_t n_layers, const float* X0, float* E,
+                            float* tmp0, float* tmp1, float* partial, lgc_stream_t stream);
+
 /* Same barrier with the epoch counter in device memory (the kernel increments *epoch_counter_dev and uses the new
  * value): capturable in a CUDA graph, replayable — all ranks must issue the same sequence of barriers. */
 int lgc_peer_barrier_dev(const int32_t* local_flags, int32_t* const* peer_flags_host, int32_t my_rank,

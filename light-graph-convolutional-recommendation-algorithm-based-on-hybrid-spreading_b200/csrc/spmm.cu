@@ -19,6 +19,8 @@
 //   * the BCAST variant stores each finished row into every peer's replica (NVLink P2P
 //     stores): the per-layer all-gather of the row-partitioned multi-GPU path is fused into
 //     the SpMM epilogue.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace lgc {
@@ -261,6 +263,87 @@ __global__ void peer_barrier_dev_kernel(const int32_t* __restrict__ local_flags,
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Small graphs: ALL K layers (+ the layer mean) in ONE cooperative launch.
+// At the ML-100K / Douban shapes a layer moves 0.4 us worth of compulsory bytes; as separate launches each layer costs
+// ~17 us (grid launch + drain + the serial (colidx, val) -> gather latency chain of the longest row).  Here the grid is
+// resident for the whole call (one CTA per SM slot, cudaLaunchCooperativeKernel), work is cut into warp-sized UNITS of
+// at most kCoopUnit non-zeros — a row, or a piece of a long row whose partial sums are combined in unit order after a
+// grid barrier (deterministic, no float atomics) — and layers are separated by grid barriers instead of launches.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kCoopUnit = 128;
+
+struct CoopParams {
+  const int32_t* rowptr;
+  const int32_t* colidx;
+  const float* val;
+  const int32_t* unit_row;    // [n_units] row of the unit
+  const int32_t* unit_start;  // [n_units] first non-zero
+  const int32_t* unit_end;    // [n_units] one past the last non-zero
+  const int32_t* unit_slot;   // [n_units] partial-sum slot, or -1 when the unit is a whole row
+  const int32_t* split_row;   // [n_split] rows cut into several units ...
+  const int32_t* split_first; // [n_split] ... their first partial slot ...
+  const int32_t* split_count; // [n_split] ... and number of partials
+  int n_units, n_split, n_layers;
+  const float* X0;
+  float* buf0;
+  float* buf1;
+  float* E;
+  float* partial;             // [n_partials][DIM]
+};
+
+template <int DIM>
+__global__ void __launch_bounds__(kThreads)
+propagate_coop_kernel(const CoopParams p) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  constexpr int LPR = DIM / 4;
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (int)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int n_warps = (int)gridDim.x * kWarpsPerBlock;
+  const float* cur = p.X0;
+  for (int l = 0; l < p.n_layers; ++l) {
+    const bool last = l == p.n_layers - 1;
+    float* out = last ? p.E : ((l & 1) ? p.buf1 : p.buf0);
+    const float alpha = last ? 1.0f / (float)(p.n_layers + 1) : 1.0f;
+    for (int u = gwarp; u < p.n_units; u += n_warps) {
+      const int row = __ldg(p.unit_row + u), slot = __ldg(p.unit_slot + u);
+      float4 acc = warp_gather_sum<DIM, 4>(p.colidx, p.val, cur, __ldg(p.unit_start + u), __ldg(p.unit_end + u), lane);
+      if (lane < LPR) {
+        if (slot < 0) {
+          const size_t off = (size_t)row * DIM + lane * 4;
+          const float4 x0 = ld_row4(p.X0 + off);
+          acc.x = alpha * (acc.x + x0.x); acc.y = alpha * (acc.y + x0.y);
+          acc.z = alpha * (acc.z + x0.z); acc.w = alpha * (acc.w + x0.w);
+          *reinterpret_cast<float4*>(out + off) = acc;
+        } else {
+          __stcg(reinterpret_cast<float4*>(p.partial + (size_t)slot * DIM + lane * 4), acc);
+        }
+      }
+    }
+    if (p.n_split > 0) {
+      grid.sync();
+      for (int s = gwarp; s < p.n_split; s += n_warps) {
+        if (lane < LPR) {
+          const int row = __ldg(p.split_row + s), first = __ldg(p.split_first + s), cnt = __ldg(p.split_count + s);
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int c = 0; c < cnt; ++c) {
+            const float4 q = __ldcg(reinterpret_cast<const float4*>(p.partial + (size_t)(first + c) * DIM + lane * 4));
+            acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+          }
+          const size_t off = (size_t)row * DIM + lane * 4;
+          const float4 x0 = ld_row4(p.X0 + off);
+          acc.x = alpha * (acc.x + x0.x); acc.y = alpha * (acc.y + x0.y);
+          acc.z = alpha * (acc.z + x0.z); acc.w = alpha * (acc.w + x0.w);
+          *reinterpret_cast<float4*>(out + off) = acc;
+        }
+      }
+    }
+    if (!last) grid.sync();
+    cur = out;
+  }
+}
+
 template <int NPEER>
 static int launch_spmm(const int32_t* rowptr, const int32_t* colidx, const float* val,
                        const int32_t* chunk_row, const int32_t* chunk_start,
@@ -442,5 +525,34 @@ extern "C" int lgc_propagate_mean(const int32_t* rowptr, const int32_t* colidx, 
     if (rc) return rc;
     cur = out;
   }
+  return LGC_OK;
+}
+
+// All K layers + layer mean in one cooperative launch (small graphs).  The unit lists are built once per graph by the
+// host side (lgcnhs_b200/ops.py: NormGraph.coop_units): units of <= 128 non-zeros, long rows cut into several units.
+extern "C" int lgc_propagate_mean_coop(const int32_t* rowptr, const int32_t* colidx, const float* val,
+                                       const int32_t* unit_row, const int32_t* unit_start, const int32_t* unit_end,
+                                       const int32_t* unit_slot, int32_t n_units, const int32_t* split_row,
+                                       const int32_t* split_first, const int32_t* split_count, int32_t n_split,
+                                       int64_t n_nodes, int32_t dim, int32_t n_layers, const float* X0, float* E,
+                                       float* tmp0, float* tmp1, float* partial, lgc_stream_t stream) {
+  LGC_REQUIRE(rowptr && colidx && val && unit_row && unit_start && unit_end && unit_slot && X0 && E, "propagate coop: null pointer");
+  LGC_REQUIRE(n_units > 0 && n_layers >= 1 && n_nodes > 0, "propagate coop: empty problem");
+  LGC_REQUIRE(n_split == 0 || (split_row && split_first && split_count && partial), "propagate coop: split lists missing");
+  LGC_REQUIRE(n_layers == 1 || (tmp0 && (n_layers == 2 || tmp1)), "propagate coop: scratch buffers missing");
+  LGC_REQUIRE(dim == 32 || dim == 64 || dim == 128, "propagate coop: embedding dim not in {32,64,128}");
+  CoopParams p{rowptr, colidx, val, unit_row, unit_start, unit_end, unit_slot, split_row, split_first, split_count,
+               n_units, n_split, n_layers, X0, tmp0, tmp1, E, partial};
+  void* fn = dim == 32 ? (void*)propagate_coop_kernel<32> : dim == 64 ? (void*)propagate_coop_kernel<64>
+                                                                      : (void*)propagate_coop_kernel<128>;
+  int per_sm = 0;
+  LGC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0));
+  if (per_sm < 1) LGC_FAIL(LGC_ERR_CUDA, "propagate coop: kernel does not fit an SM");
+  int64_t grid = (int64_t)num_sms() * (per_sm > 4 ? 4 : per_sm);
+  const int64_t want = ceil_div(n_units, kWarpsPerBlock);
+  if (grid > want) grid = want;
+  void* args[] = {(void*)&p};
+  LGC_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(kThreads), args, 0, (cudaStream_t)stream));
+  note_launch();
   return LGC_OK;
 }

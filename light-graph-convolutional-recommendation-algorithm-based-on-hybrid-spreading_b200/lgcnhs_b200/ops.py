@@ -78,6 +78,7 @@ class NormGraph:
         self.n_chunks = int(n_chunks.value)
         self.chunk_row = self.chunk_row[: max(self.n_chunks, 1)].clone()
         self.chunk_start = self.chunk_start[: max(self.n_chunks, 1)].clone()
+        self._coop = None
         self._scratch: dict[int, tuple[torch.Tensor, torch.Tensor]] = {}
         self._orders: dict[tuple[int, int], torch.Tensor] = {}
         self._long_rows: dict[tuple[int, int], int] = {}
@@ -114,7 +115,7 @@ class NormGraph:
         t.chunk_row = crow.to(torch.int32) if t.n_chunks else torch.zeros(1, dtype=torch.int32, device=dev)
         t.chunk_start = ((rowptr[:-1][crow] + within * CHUNK).to(torch.int32) if t.n_chunks
                          else torch.zeros(1, dtype=torch.int32, device=dev))
-        t._scratch, t._orders, t._long_rows = {}, {}, {}
+        t._scratch, t._orders, t._long_rows, t._coop = {}, {}, {}, None
         t.use_row_order = self.use_row_order
         return t
 
@@ -191,9 +192,45 @@ class NormGraph:
                                          arr, len(peer_ptrs), _ptr(partial), _ptr(counters), _stream()),
               "spmm layer bcast")
 
+    COOP_MAX_NNZ = 1_000_000    # graphs up to this many non-zeros run all K layers in one cooperative launch
+    COOP_UNIT = 128
+
+    def coop_units(self):
+        """Work units of the one-launch K-layer kernel (lgc_propagate_mean_coop), built once per graph: every row is cut
+        into pieces of <= COOP_UNIT non-zeros, longest rows first; pieces of a cut row own consecutive partial slots."""
+        if self._coop is None:
+            dev = self.device
+            rp = self.rowptr.to(torch.int64)
+            deg = rp[1:] - rp[:-1]
+            order = torch.argsort(deg, descending=True, stable=True)
+            deg_o = deg[order]
+            pieces = torch.clamp((deg_o + self.COOP_UNIT - 1) // self.COOP_UNIT, min=1)
+            unit_row = torch.repeat_interleave(order, pieces)
+            first_unit = torch.cumsum(pieces, 0) - pieces
+            within = torch.arange(int(pieces.sum()), device=dev) - torch.repeat_interleave(first_unit, pieces)
+            start = rp[:-1][unit_row] + within * self.COOP_UNIT
+            end = torch.minimum(start + self.COOP_UNIT, rp[1:][unit_row])
+            is_split = pieces > 1
+            n_split = int(is_split.sum())
+            split_pieces = pieces[is_split]
+            split_first = torch.cumsum(split_pieces, 0) - split_pieces
+            slot_of_row = torch.full((self.n_nodes,), -1, dtype=torch.int64, device=dev)
+            slot_of_row[order[is_split]] = split_first
+            slot = torch.where(slot_of_row[unit_row] >= 0, slot_of_row[unit_row] + within, torch.full_like(within, -1))
+            i32 = lambda t: t.to(torch.int32).contiguous()  # noqa: E731
+            self._coop = {"unit_row": i32(unit_row), "start": i32(start), "end": i32(end), "slot": i32(slot),
+                          "split_row": i32(order[is_split]) if n_split else None,
+                          "split_first": i32(split_first) if n_split else None,
+                          "split_count": i32(split_pieces) if n_split else None,
+                          "n_units": int(unit_row.numel()), "n_split": n_split, "n_partials": int(split_pieces.sum()) if n_split else 0,
+                          "partial": {}}
+        return self._coop
+
     def propagate_mean(self, X0: torch.Tensor, n_layers: int, out: Optional[torch.Tensor] = None,
-                       tmp: Optional[tuple[torch.Tensor, torch.Tensor]] = None) -> torch.Tensor:
-        """E = mean_l(A_hat^l X0), l = 0..n_layers (model/LightGCN/model.py:56-69)."""
+                       tmp: Optional[tuple[torch.Tensor, torch.Tensor]] = None, coop: Optional[bool] = None) -> torch.Tensor:
+        """E = mean_l(A_hat^l X0), l = 0..n_layers (model/LightGCN/model.py:56-69).
+        coop (default: graphs with <= COOP_MAX_NNZ non-zeros, LGCNHS_NO_COOP=1 disables): all layers in ONE cooperative
+        launch with grid barriers between them (small graphs are launch-latency bound)."""
         X0 = _req(X0, torch.float32, "X0")
         n, dim = self.n_nodes, int(X0.shape[1])
         if X0.shape[0] != n:
@@ -202,6 +239,19 @@ class NormGraph:
             out = torch.empty_like(X0)
         if tmp is None:
             tmp = (torch.empty_like(X0), torch.empty_like(X0))
+        if coop is None:
+            coop = 0 < self.nnz <= self.COOP_MAX_NNZ and n_layers >= 1 and os.environ.get("LGCNHS_NO_COOP", "0") != "1"
+        if coop:
+            cu = self.coop_units()
+            part = cu["partial"].get(dim)
+            if part is None:
+                part = cu["partial"][dim] = torch.empty(max(cu["n_partials"], 1) * dim, dtype=torch.float32, device=self.device)
+            check(lib().lgc_propagate_mean_coop(_ptr(self.rowptr), _ptr(self.colidx), _ptr(self.val), _ptr(cu["unit_row"]),
+                                                _ptr(cu["start"]), _ptr(cu["end"]), _ptr(cu["slot"]), cu["n_units"],
+                                                _ptr(cu["split_row"]), _ptr(cu["split_first"]), _ptr(cu["split_count"]),
+                                                cu["n_split"], n, dim, int(n_layers), _ptr(X0), _ptr(out), _ptr(tmp[0]),
+                                                _ptr(tmp[1]), _ptr(part), _stream()), "propagate_mean (cooperative)")
+            return out
         partial, counters = self._scr(dim)
         check(lib().lgc_propagate_mean(_ptr(self.rowptr), _ptr(self.colidx), _ptr(self.val), _ptr(self.chunk_row),
                                        _ptr(self.chunk_start), _ptr(self.row_chunk_base), self.n_chunks, n, dim,

@@ -180,3 +180,28 @@ def test_pipelined_host_table_propagation(dev):
         assert torch.equal(o, g.propagate_mean(x.to(dev), 3).cpu())
     with pytest.raises(RuntimeError):
         pipe.submit(torch.randn(n, 64), outs[0])          # unpinned host memory is refused
+
+
+@pytest.mark.parametrize("name,hub,dim,layers", [("tiny", 0, 64, 3), ("small", 300, 64, 3), ("ml-100k", 0, 64, 3),
+                                                 ("ml-100k", 943, 32, 2), ("ml-100k", 943, 128, 1), ("douban", 0, 64, 4)])
+def test_cooperative_k_layer_kernel(dev, name, hub, dim, layers):
+    """lgc_propagate_mean_coop (all layers in one cooperative launch, rows cut into <= 128-nnz units, long rows combined
+    from partials in unit order) vs the oracle's per-layer tensors and vs the per-layer launches."""
+    from lgcnhs_b200.ops import NormGraph
+
+    d, adj = make_graph(name, hub)
+    n = d.n_users + d.n_items
+    g = NormGraph(adj.to(dev), n)
+    torch.manual_seed(3)
+    x0 = torch.randn(n, dim) * 0.1
+    ref = sum(O.propagate_layers(x0, adj, layers)) / (layers + 1)
+    absref = sum(O.propagate_layers(x0.abs(), adj, layers)) / (layers + 1)
+    got = g.propagate_mean(x0.to(dev), layers, coop=True)
+    assert_close(got, ref, f"cooperative K-layer mean ({name})", sum_abs=absref)
+    plain = g.propagate_mean(x0.to(dev), layers, coop=False)
+    assert_close(got, plain, "cooperative vs per-layer launches", sum_abs=absref)
+    assert torch.equal(got, g.propagate_mean(x0.to(dev), layers, coop=True))          # deterministic
+    cu = g.coop_units()
+    assert int((cu["end"] - cu["start"]).max()) <= 128 and int((cu["end"] - cu["start"]).sum()) == g.nnz
+    if hub:
+        assert cu["n_split"] >= 1
