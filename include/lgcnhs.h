@@ -411,6 +411,15 @@ int lgc_spmm_layer_bcast(const int32_t* rowptr, const int32_t* colidx, const flo
                          float* const* peer_Y_host, int32_t n_peers, float* partial,
                          int32_t* counters, lgc_stream_t stream);
 
+/* lgc_bpr_fwd_bwd with a DETERMINISTIC gradient scatter (bit-reproducible training): every (triplet, role) writes its
+ * gradient row to a compact per-entry array, then the first entry of every distinct table row adds its duplicates in
+ * ascending entry order and stores the sums with plain stores — no floating-point atomics.  gE / gX0 must be zero on
+ * entry in the rows the batch does not touch (they are not written).  workspace: lgc_bpr_det_workspace_bytes(). */
+int64_t lgc_bpr_det_workspace_bytes(int64_t batch, int32_t dim);
+int lgc_bpr_fwd_bwd_det(const float* E, const float* X0, int64_t n_users, int64_t n_items, int32_t dim,
+                        const int64_t* users, const int64_t* pos, const int64_t* neg, int64_t batch, float eps,
+                        float grad_scale, float* loss_out, float* gE, float* gX0, float* scratch,
+                        void* workspace, int64_t workspace_bytes, lgc_stream_t stream);
 /* Adam (torch.optim.Adam.step, model/LightGCN/train.py:104,144) on elements [offset, offset + n) of the parameter
  * table with the step-dependent scalars in device memory (lgc_adam_hyper_step), the gradient given as grad + grad2
  * (grad2 may be null: the propagated gradient and the sparse direct rows need no separate add pass), and the updated

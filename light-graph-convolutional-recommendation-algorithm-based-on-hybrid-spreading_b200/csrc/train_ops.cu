@@ -125,6 +125,131 @@ bpr_kernel(BprPtrs P, int64_t batch, float eps, float grad_scale, float* __restr
   }
 }
 
+// ---- deterministic gradient scatter (bit-reproducible training) ------------------------------------------------------
+// The atomicAdd scatter above sums the contributions of duplicate rows of a batch in an order that changes from run to
+// run.  Deterministic variant, two kernels:
+//   1. bpr_compact_kernel: the same forward/backward math, but every (triplet, role) writes its gradient row into
+//      compact per-entry arrays (entry e = 3 b + role; role 0 = user, 1 = positive item, 2 = negative item);
+//   2. bpr_reduce_kernel: one sub-group of DIM/4 lanes per entry; the FIRST entry of every distinct table row (no
+//      earlier entry with the same row) adds the rows of all its duplicates in ascending entry order and stores the
+//      sums into gE / gX0 with plain stores.  O(entries^2 / 16) integer compares in L1 — 0.6 M for B = 1024.
+template <int DIM>
+__global__ void __launch_bounds__(kBprThreads)
+bpr_compact_kernel(const float* __restrict__ E, const float* __restrict__ X0, int64_t n_users,
+                   const int64_t* __restrict__ users, const int64_t* __restrict__ pos, const int64_t* __restrict__ neg,
+                   int64_t batch, float eps, float grad_scale, float* __restrict__ loss_out, float* __restrict__ scratch,
+                   int32_t* __restrict__ ent_row, float* __restrict__ ent_gE, float* __restrict__ ent_gX) {
+  constexpr int LPR = DIM / 4;
+  constexpr int TPB = kBprThreads / LPR;
+  const int sub = threadIdx.x / LPR, li = threadIdx.x % LPR;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float sp_sum = 0.f, reg_sum = 0.f;
+  const float inv_b = 1.0f / (float)batch;
+  for (int64_t b0 = (int64_t)blockIdx.x * TPB; b0 < batch; b0 += (int64_t)gridDim.x * TPB) {
+    const int64_t b = b0 + sub;
+    const bool ok = b < batch;
+    float4 uf = make_float4(0, 0, 0, 0), pf = uf, nf = uf, u0 = uf, p0 = uf, n0 = uf;
+    int64_t ru = 0, rp = 0, rn = 0;
+    if (ok) {
+      ru = users[b]; rp = n_users + pos[b]; rn = n_users + neg[b];
+      uf = ld4(E + ru * DIM + li * 4); pf = ld4(E + rp * DIM + li * 4); nf = ld4(E + rn * DIM + li * 4);
+      u0 = ld4(X0 + ru * DIM + li * 4); p0 = ld4(X0 + rp * DIM + li * 4); n0 = ld4(X0 + rn * DIM + li * 4);
+    }
+    float sp = dot4(uf, pf), sn = dot4(uf, nf);
+    float rg = dot4(u0, u0) + dot4(p0, p0) + dot4(n0, n0);
+#pragma unroll
+    for (int off = LPR / 2; off >= 1; off >>= 1) {
+      sp += __shfl_xor_sync(0xffffffffu, sp, off);
+      sn += __shfl_xor_sync(0xffffffffu, sn, off);
+      rg += __shfl_xor_sync(0xffffffffu, rg, off);
+    }
+    const float x = sp - sn;
+    if (ok && li == 0) {
+      sp_sum += softplus_t(x);
+      reg_sum += rg;
+    }
+    if (ok) {
+      const float g = -grad_scale * inv_b * softplus_grad_t(x);
+      const float r = 2.f * eps * grad_scale;
+      const size_t e0 = (size_t)(3 * b) * DIM + li * 4;
+      if (li == 0) { ent_row[3 * b] = (int32_t)ru; ent_row[3 * b + 1] = (int32_t)rp; ent_row[3 * b + 2] = (int32_t)rn; }
+      *reinterpret_cast<float4*>(ent_gE + e0) = make_float4(g * (pf.x - nf.x), g * (pf.y - nf.y), g * (pf.z - nf.z), g * (pf.w - nf.w));
+      *reinterpret_cast<float4*>(ent_gE + e0 + DIM) = make_float4(g * uf.x, g * uf.y, g * uf.z, g * uf.w);
+      *reinterpret_cast<float4*>(ent_gE + e0 + 2 * DIM) = make_float4(-g * uf.x, -g * uf.y, -g * uf.z, -g * uf.w);
+      *reinterpret_cast<float4*>(ent_gX + e0) = make_float4(r * u0.x, r * u0.y, r * u0.z, r * u0.w);
+      *reinterpret_cast<float4*>(ent_gX + e0 + DIM) = make_float4(r * p0.x, r * p0.y, r * p0.z, r * p0.w);
+      *reinterpret_cast<float4*>(ent_gX + e0 + 2 * DIM) = make_float4(r * n0.x, r * n0.y, r * n0.z, r * n0.w);
+    }
+  }
+  __shared__ float s_sp[kBprThreads / 32], s_rg[kBprThreads / 32];
+  __shared__ int s_last;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    sp_sum += __shfl_xor_sync(0xffffffffu, sp_sum, off);
+    reg_sum += __shfl_xor_sync(0xffffffffu, reg_sum, off);
+  }
+  if (lane == 0) { s_sp[warp] = sp_sum; s_rg[warp] = reg_sum; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, c = 0.f;
+    for (int w = 0; w < kBprThreads / 32; ++w) { a += s_sp[w]; c += s_rg[w]; }
+    float* part = scratch + 2;
+    __stcg(part + 2 * blockIdx.x, a);
+    __stcg(part + 2 * blockIdx.x + 1, c);
+    __threadfence();
+    const int ticket = atomicAdd(reinterpret_cast<int*>(scratch), 1);
+    s_last = (ticket == (int)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    float a = 0.f, c = 0.f;
+    const float* part = scratch + 2;
+    for (unsigned i = 0; i < gridDim.x; ++i) { a += __ldcg(part + 2 * i); c += __ldcg(part + 2 * i + 1); }
+    const float bpr = -a * inv_b;
+    loss_out[0] = bpr + eps * c;
+    loss_out[1] = bpr;
+    *reinterpret_cast<int*>(scratch) = 0;
+  }
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(kBprThreads)
+bpr_reduce_kernel(const int32_t* __restrict__ ent_row, const float* __restrict__ ent_gE, const float* __restrict__ ent_gX,
+                  int n_ent, float* __restrict__ gE, float* __restrict__ gX) {
+  constexpr int LPR = DIM / 4;
+  const int e = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR);
+  const int li = threadIdx.x % LPR;
+  if (e >= n_ent) return;                         // whole sub-groups leave together (LPR divides the block size)
+  const int row = __ldg(ent_row + e);
+  // a sub-group is LPR consecutive lanes of one warp: its lanes vote with a sub-group mask
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned gmask = (LPR == 32 ? 0xffffffffu : ((1u << LPR) - 1u) << (lane & ~(unsigned)(LPR - 1)));
+  bool dup = false;
+  for (int j0 = 0; j0 < e; j0 += LPR) {
+    const int j = j0 + li;
+    dup |= (j < e) && (__ldg(ent_row + j) == row);
+  }
+  if (__any_sync(gmask, dup)) return;             // not the first entry of its row
+  float4 a = *reinterpret_cast<const float4*>(ent_gE + (size_t)e * DIM + li * 4);
+  float4 x = *reinterpret_cast<const float4*>(ent_gX + (size_t)e * DIM + li * 4);
+  for (int j0 = e + 1; j0 < n_ent; j0 += LPR) {
+    const int j = j0 + li;
+    const bool hit = (j < n_ent) && (__ldg(ent_row + j) == row);
+    unsigned m = (__ballot_sync(gmask, hit) & gmask) >> (lane & ~(unsigned)(LPR - 1));
+    while (m) {                                   // duplicates in ascending entry order
+      const int jj = j0 + (__ffs(m) - 1);
+      m &= m - 1u;
+      const float4 b = *reinterpret_cast<const float4*>(ent_gE + (size_t)jj * DIM + li * 4);
+      const float4 y = *reinterpret_cast<const float4*>(ent_gX + (size_t)jj * DIM + li * 4);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+    }
+  }
+  *reinterpret_cast<float4*>(gE + (size_t)row * DIM + li * 4) = a;
+  *reinterpret_cast<float4*>(gX + (size_t)row * DIM + li * 4) = x;
+}
+
 static int bpr_grid(int64_t batch, int dim) {
   const int tpb = kBprThreads / (dim / 4);
   int64_t g = ceil_div(batch, tpb);
@@ -366,5 +491,45 @@ extern "C" int lgc_zero_rows(float* a, float* b, int32_t dim, const int64_t* use
   const int64_t threads = 3 * batch * (dim / 4);
   zero_rows_kernel<<<(unsigned)ceil_div(threads, 256), 256, 0, (cudaStream_t)stream>>>(a, b, dim, users, pos, neg, batch, n_users);
   LGC_LAUNCH_CHECK("zero_rows_kernel");
+  return LGC_OK;
+}
+
+extern "C" int64_t lgc_bpr_det_workspace_bytes(int64_t batch, int32_t dim) {
+  if (batch <= 0 || dim <= 0) return 0;
+  return (int64_t)(align_up((size_t)3 * batch * sizeof(int32_t), 256) + 2 * align_up((size_t)3 * batch * dim * sizeof(float), 256));
+}
+
+extern "C" int lgc_bpr_fwd_bwd_det(const float* E, const float* X0, int64_t n_users, int64_t n_items, int32_t dim,
+                                   const int64_t* users, const int64_t* pos, const int64_t* neg, int64_t batch, float eps,
+                                   float grad_scale, float* loss_out, float* gE, float* gX0, float* scratch,
+                                   void* workspace, int64_t workspace_bytes, lgc_stream_t stream_) {
+  LGC_REQUIRE(E && X0 && users && pos && neg && loss_out && scratch && gE && gX0 && workspace, "bpr det: null pointer");
+  LGC_REQUIRE(batch > 0 && batch <= 65536 && n_users > 0 && n_items > 0 && n_users + n_items < (1ll << 31),
+              "bpr det: batch must be in [1, 65536] and the tables addressable with int32");
+  LGC_REQUIRE(workspace_bytes >= lgc_bpr_det_workspace_bytes(batch, dim) && ((uintptr_t)workspace & 255) == 0,
+              "bpr det: workspace too small or misaligned");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  char* base = reinterpret_cast<char*>(workspace);
+  int32_t* ent_row = reinterpret_cast<int32_t*>(base);
+  const size_t o1 = align_up((size_t)3 * batch * sizeof(int32_t), 256);
+  const size_t o2 = o1 + align_up((size_t)3 * batch * dim * sizeof(float), 256);
+  float* ent_gE = reinterpret_cast<float*>(base + o1);
+  float* ent_gX = reinterpret_cast<float*>(base + o2);
+  const int grid = bpr_grid(batch, dim);
+  const int n_ent = (int)(3 * batch);
+  const unsigned rgrid = (unsigned)ceil_div((int64_t)n_ent * (dim / 4), kBprThreads);
+  switch (dim) {
+#define LGC_BPR_DET(D)                                                                                                \
+  case D:                                                                                                             \
+    bpr_compact_kernel<D><<<grid, kBprThreads, 0, stream>>>(E, X0, n_users, users, pos, neg, batch, eps, grad_scale,   \
+                                                            loss_out, scratch, ent_row, ent_gE, ent_gX);              \
+    LGC_LAUNCH_CHECK("bpr_compact_kernel");                                                                           \
+    bpr_reduce_kernel<D><<<rgrid, kBprThreads, 0, stream>>>(ent_row, ent_gE, ent_gX, n_ent, gE, gX0);                  \
+    LGC_LAUNCH_CHECK("bpr_reduce_kernel");                                                                            \
+    break;
+    LGC_BPR_DET(32) LGC_BPR_DET(64) LGC_BPR_DET(128)
+#undef LGC_BPR_DET
+    default: LGC_FAIL(LGC_ERR_UNSUPPORTED, "bpr det: embedding dim %d not in {32,64,128}", dim);
+  }
   return LGC_OK;
 }

@@ -41,6 +41,8 @@ _SIGS = {
                                           _p]),
     "lgc_bpr_scratch_floats": (_i64, [_i64]),
     "lgc_bpr_fwd_bwd": (C.c_int, [_p, _p, _i64, _i64, _i32, _p, _p, _p, _i64, _f32, _f32, _p, _p, _p, _p, _p]),
+    "lgc_bpr_det_workspace_bytes": (_i64, [_i64, _i32]),
+    "lgc_bpr_fwd_bwd_det": (C.c_int, [_p, _p, _i64, _i64, _i32, _p, _p, _p, _i64, _f32, _f32, _p, _p, _p, _p, _p, _i64, _p]),
     "lgc_bpr_rows": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i32, _f32, _f32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "lgc_adam_step": (C.c_int, [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _p]),
     "lgc_adam_hyper_step": (C.c_int, [_p, _p, _f32, _f32, _p, _p]),

@@ -321,6 +321,29 @@ def bpr_fwd_bwd(E: torch.Tensor, X0: torch.Tensor, n_users: int, n_items: int, u
     return loss
 
 
+_bpr_det_ws: dict = {}
+
+
+def bpr_fwd_bwd_det(E: torch.Tensor, X0: torch.Tensor, n_users: int, n_items: int, users: torch.Tensor, pos: torch.Tensor,
+                    neg: torch.Tensor, eps: float, gE: torch.Tensor, gX0: torch.Tensor, grad_scale: float = 1.0,
+                    loss_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """bpr_fwd_bwd with the deterministic (atomic-free) gradient scatter: bit-identical gradients from run to run."""
+    E = _req(E, torch.float32, "E")
+    X0 = _req(X0, torch.float32, "X0")
+    dim, batch = int(E.shape[1]), int(users.numel())
+    for t, nm in ((users, "users"), (pos, "pos"), (neg, "neg")):
+        _req(t, torch.int64, nm)
+    loss = torch.empty(2, dtype=torch.float32, device=E.device) if loss_out is None else loss_out
+    nbytes = int(lib().lgc_bpr_det_workspace_bytes(batch, dim))
+    ws = _bpr_det_ws.get((E.device, batch, dim))
+    if ws is None:
+        ws = _bpr_det_ws[(E.device, batch, dim)] = torch.empty(nbytes, dtype=torch.uint8, device=E.device)
+    check(lib().lgc_bpr_fwd_bwd_det(_ptr(E), _ptr(X0), n_users, n_items, dim, _ptr(users), _ptr(pos), _ptr(neg), batch,
+                                    float(eps), float(grad_scale), _ptr(loss), _ptr(gE), _ptr(gX0), _ptr(_bpr_scr(E.device)),
+                                    _ptr(ws), nbytes, _stream()), "bpr (deterministic)")
+    return loss
+
+
 def bpr_rows(rows: Sequence[torch.Tensor], eps: float, grads: Optional[Sequence[torch.Tensor]] = None,
              grad_scale: float = 1.0) -> torch.Tensor:
     """rows = (u_f, u_0, p_f, p_0, n_f, n_0), each (B, dim) fp32."""

@@ -41,7 +41,8 @@ class FusedBPRTrainer:
     (no reduction needed).  All ranks must draw the same mini-batches (same torch seed)."""
 
     def __init__(self, model, train_adj_index: torch.Tensor, lr: float, eps_reg: float,
-                 betas=(0.9, 0.999), adam_eps: float = 1e-8, graph: Optional[bool] = None, distributed: bool = False):
+                 betas=(0.9, 0.999), adam_eps: float = 1e-8, graph: Optional[bool] = None, distributed: bool = False,
+                 deterministic: Optional[bool] = None):
         self.model = model
         self.U, self.M = model.user_num, model.item_num
         self.N, self.D, self.K = self.U + self.M, model.embedding_dim, model.layers
@@ -54,6 +55,12 @@ class FusedBPRTrainer:
         dev = model.users_emb.weight.device
         self.dev = dev
         self.distributed = bool(distributed)
+        # deterministic=True (or LGCNHS_DETERMINISTIC=1): atomic-free gradient scatter -> the whole step is bit-reproducible
+        # (the SpMM, the loss reduction and Adam already are); always on in distributed mode, where every rank must hand
+        # the gradient propagation the SAME replicated gE
+        if deterministic is None:
+            deterministic = self.distributed or os.environ.get("LGCNHS_DETERMINISTIC", "0") == "1"
+        self.deterministic = bool(deterministic)
         z = lambda: torch.zeros((self.N, self.D), dtype=torch.float32, device=dev)  # noqa: E731
         # one weight table; the module's parameters become views of it (same Parameter objects, same values)
         self.X0 = z()
@@ -128,7 +135,8 @@ class FusedBPRTrainer:
         """Everything of one step that touches the device; identical in eager and captured form.  gE / gX are all-zero
         on entry and on exit."""
         X0, E = self.forward_embeddings()
-        ops.bpr_fwd_bwd(E, X0, self.U, self.M, users, pos, neg, self.eps_reg, self.gE, self.gX, loss_out=self.loss_dev)
+        bpr = ops.bpr_fwd_bwd_det if self.deterministic else ops.bpr_fwd_bwd
+        bpr(E, X0, self.U, self.M, users, pos, neg, self.eps_reg, self.gE, self.gX, loss_out=self.loss_dev)
         # dL/dX0 = mean_l (A^T)^l dL/dE  +  regulariser rows
         if self.distributed:
             gP = self.prop.propagate_mean(self.gE, self.K, result=1)
