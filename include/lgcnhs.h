@@ -99,6 +99,10 @@ int lgc_spmm_layer(const int32_t* rowptr, const int32_t* colidx, const float* va
 
 /* Tuning knob: independent 128-bit gathers in flight per lane for dim 64 (2, 4 or 8). */
 int lgc_spmm_config(int32_t unroll);
+/* Experimental (dim 64): 1 = the colidx array passed to the SpMM entry points carries a "hot source row" flag in bit 31
+ * (the few hundred highest-degree nodes): hot rows are gathered with L1 evict-last, all others bypass L1.  0 = plain
+ * column indices (default).  Process-global, like the other tuning knobs. */
+int lgc_spmm_hot_mode(int32_t on);
 /* Tuning knob: override of the per-call long_row for the launches that follow (in [LGC_LONG_ROW, 2048];
  * 0 = use the per-call value).  The chunk lists always cover rows > LGC_LONG_ROW. */
 int lgc_spmm_long_row(int32_t long_row);

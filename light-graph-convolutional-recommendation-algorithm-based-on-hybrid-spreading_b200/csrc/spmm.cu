@@ -31,6 +31,7 @@ constexpr int kMaxPeers = 8;
 
 static int g_spmm_long_row = 0;  // override of the per-call warp-per-row threshold (lgc_spmm_long_row); 0 = none
 static int g_spmm_unroll = 0;  // gathers in flight per lane for DIM=64; 0 = choose by grid size (lgc_spmm_config)
+static int g_spmm_hot = 0;     // 1: colidx carries the hot-row flag in bit 31 (lgc_spmm_hot_mode), DIM = 64 only
 
 struct PeerPtrs {
   float* y[kMaxPeers];
@@ -39,13 +40,26 @@ struct PeerPtrs {
 __device__ __forceinline__ float4 ld_row4(const float* p) {
   return __ldg(reinterpret_cast<const float4*>(p));
 }
+// Gathers with an L1 policy chosen per source row (HOT mode): rows of the few hundred highest-degree nodes — a fifth of all
+// gathers under the Zipf-like item popularity — are kept in L1 (evict-last), all other rows bypass it (no-allocate), so
+// the hot set is not flushed by the 80 % of gathers that are never re-referenced soon.  Bit 31 of colidx marks a hot row.
+__device__ __forceinline__ float4 ld_row4_hot(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ld_row4_cold(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
 
 // Sum of val[e] * X[colidx[e], :] over e in [start, end) for one warp.  On return every
 // lane li of every sub-group holds the full sum for columns [4*li, 4*li+4).
 // UN independent 128-bit gathers are in flight per lane, and the (colidx, val) metadata of the
 // next 32 non-zeros is requested before the gathers of the current 32 are issued, so the
 // dependent metadata -> gather chain is overlapped.
-template <int DIM, int UN>
+template <int DIM, int UN, bool HOT = false>
 __device__ __forceinline__ float4 warp_gather_sum(const int32_t* __restrict__ colidx,
                                                   const float* __restrict__ val,
                                                   const float* __restrict__ X, int start, int end,
@@ -74,11 +88,20 @@ __device__ __forceinline__ float4 warp_gather_sum(const int32_t* __restrict__ co
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
         const int jj = j + u * SUB + sub;
-        const int cc = __shfl_sync(0xffffffffu, c, jj & 31);
+        int cc = __shfl_sync(0xffffffffu, c, jj & 31);
         const float vv = __shfl_sync(0xffffffffu, v, jj & 31);
         const bool ok = jj < n;
         w[u] = ok ? vv : 0.f;
-        x[u] = ok ? ld_row4(X + (size_t)cc * DIM + li * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (HOT) {
+          const bool hot = cc < 0;
+          cc &= 0x7fffffff;
+          const float* src = X + (size_t)cc * DIM + li * 4;
+          x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok && hot) x[u] = ld_row4_hot(src);
+          if (ok && !hot) x[u] = ld_row4_cold(src);
+        } else {
+          x[u] = ok ? ld_row4(X + (size_t)cc * DIM + li * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
@@ -112,7 +135,7 @@ __device__ __forceinline__ void store_row4(float* Y, const PeerPtrs& peers, size
   }
 }
 
-template <int DIM, int NPEER, int UN>
+template <int DIM, int NPEER, int UN, bool HOT = false>
 __global__ void __launch_bounds__(kThreads)
 spmm_layer_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                   const float* __restrict__ val, const int32_t* __restrict__ chunk_row,
@@ -134,7 +157,7 @@ spmm_layer_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
     const int row = row_order ? __ldg(row_order + (slot - row_begin)) : slot;
     const int start = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
     if (end - start > long_row) return;  // handled by the chunk CTAs
-    float4 acc = warp_gather_sum<DIM, UN>(colidx, val, X, start, end, lane);
+    float4 acc = warp_gather_sum<DIM, UN, HOT>(colidx, val, X, start, end, lane);
     if (lane < LPR) {
       const size_t off = (size_t)row * DIM + lane * 4;
       if (beta != 0.f) {
@@ -161,7 +184,7 @@ spmm_layer_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
   const int cend = min(cstart + LGC_CHUNK, rend);
   constexpr int PER_WARP = LGC_CHUNK / kWarpsPerBlock;
   const int wstart = min(cstart + warp * PER_WARP, cend), wend = min(wstart + PER_WARP, cend);
-  float4 acc = warp_gather_sum<DIM, UN>(colidx, val, X, wstart, wend, lane);
+  float4 acc = warp_gather_sum<DIM, UN, HOT>(colidx, val, X, wstart, wend, lane);
   if (lane < LPR) *reinterpret_cast<float4*>(&s_part[warp][lane * 4]) = acc;
   __syncthreads();
   const int nch = (rend - rstart + LGC_CHUNK - 1) / LGC_CHUNK;
@@ -376,7 +399,17 @@ static int launch_spmm(const int32_t* rowptr, const int32_t* colidx, const float
         // (32 regs, 64 warps/SM) beats per-warp ILP; with a single wave the deeper unroll wins
         int un = g_spmm_unroll;
         if (un == 0) un = grid > (int64_t)num_sms() * 8 * 2 ? 2 : 4;
-        if (un == 8) LGC_SPMM_LAUNCH(64, 8);
+        if (g_spmm_hot) {
+          if (un == 2) {
+            spmm_layer_kernel<64, NPEER, 2, true><<<(unsigned)grid, kThreads, 0, stream>>>(
+                rowptr, colidx, val, chunk_row, chunk_start, row_chunk_base, chunk_begin, n_chunk_blocks, (int)row_begin,
+                (int)row_end, row_order, X, X0, alpha, beta, Y, peers, partial, counters, long_row);
+          } else {
+            spmm_layer_kernel<64, NPEER, 4, true><<<(unsigned)grid, kThreads, 0, stream>>>(
+                rowptr, colidx, val, chunk_row, chunk_start, row_chunk_base, chunk_begin, n_chunk_blocks, (int)row_begin,
+                (int)row_end, row_order, X, X0, alpha, beta, Y, peers, partial, counters, long_row);
+          }
+        } else if (un == 8) LGC_SPMM_LAUNCH(64, 8);
         else if (un == 2) LGC_SPMM_LAUNCH(64, 2);
         else LGC_SPMM_LAUNCH(64, 4);
       }
@@ -412,6 +445,11 @@ using namespace lgc;
 extern "C" int lgc_spmm_config(int32_t unroll) {
   LGC_REQUIRE(unroll == 0 || unroll == 2 || unroll == 4 || unroll == 8, "spmm config: unroll must be 0 (auto), 2, 4 or 8");
   g_spmm_unroll = unroll;
+  return LGC_OK;
+}
+
+extern "C" int lgc_spmm_hot_mode(int32_t on) {
+  g_spmm_hot = on ? 1 : 0;
   return LGC_OK;
 }
 

@@ -36,6 +36,7 @@ _SIGS = {
     "lgc_zero_rows": (C.c_int, [_p, _p, _i32, _p, _p, _p, _i64, _i64, _p]),
     "lgc_spmm_config": (C.c_int, [_i32]),
     "lgc_spmm_long_row": (C.c_int, [_i32]),
+    "lgc_spmm_hot_mode": (C.c_int, [_i32]),
     "lgc_propagate_mean": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i64, _i32, _i32, _p, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "lgc_propagate_mean_coop": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _i32, _i64, _i32, _i32, _p, _p, _p, _p, _p,
                                           _p]),
