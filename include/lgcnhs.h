@@ -99,10 +99,27 @@ int lgc_spmm_layer(const int32_t* rowptr, const int32_t* colidx, const float* va
 
 /* Tuning knob: independent 128-bit gathers in flight per lane for dim 64 (2, 4 or 8). */
 int lgc_spmm_config(int32_t unroll);
-/* Experimental (dim 64): 1 = the colidx array passed to the SpMM entry points carries a "hot source row" flag in bit 31
- * (the few hundred highest-degree nodes): hot rows are gathered with L1 evict-last, all others bypass L1.  0 = plain
- * column indices (default).  Process-global, like the other tuning knobs. */
-int lgc_spmm_hot_mode(int32_t on);
+/* ------------------------------------------------------------------------------------
+ * (N2) Format ingestion in front of both hot paths, as own kernels (stable LSD radix sort of 64-bit
+ * keys + exclusive scan, csrc/ingest.cuh).
+ * lgc_seen_csr: (user, item) pairs -> DEDUPLICATED int32 CSR over all users (rowptr[n_users+1],
+ *   item ids ascending per row; idx needs room for n_pairs entries; *n_unique_host = entries
+ *   written).  It is the per-user item list the reference builds with Python loops:
+ *   getUserItemsDictByDataframe / getUserItemsDictByEdgeIndex (utils/trans.py:51-80), the exclusion
+ *   pairs of model/LightGCN/recommend.py:92-111 and the positive lists np.isin searches in
+ *   structured_negative_sampling (model/LightGCN/loss.py:58).  One D2H sync (the count).
+ * lgc_sort_u64: stable ascending sort of the low `bits` bits of 64-bit keys, in place (tmp: n keys).
+ * ---------------------------------------------------------------------------------- */
+int lgc_seen_csr_workspace_bytes(int64_t n_pairs, size_t* bytes_host);
+int lgc_seen_csr(const int64_t* users, const int64_t* items, int64_t n_pairs, int64_t n_users,
+                 int64_t n_items, int32_t* rowptr, int32_t* idx, int64_t* n_unique_host,
+                 void* workspace, size_t workspace_bytes, lgc_stream_t stream);
+int lgc_sort_u64_workspace_bytes(int64_t n, size_t* bytes_host);
+int lgc_sort_u64(uint64_t* keys, uint64_t* tmp, int64_t n, int32_t bits, void* workspace,
+                 size_t workspace_bytes, lgc_stream_t stream);
+
+/* Tuning knob of lgc_propagate_mean_coop: resident CTAs per SM (1..8, default 2); fewer CTAs = cheaper grid barriers. */
+int lgc_coop_config(int32_t ctas_per_sm);
 /* Tuning knob: override of the per-call long_row for the launches that follow (in [LGC_LONG_ROW, 2048];
  * 0 = use the per-call value).  The chunk lists always cover rows > LGC_LONG_ROW. */
 int lgc_spmm_long_row(int32_t long_row);

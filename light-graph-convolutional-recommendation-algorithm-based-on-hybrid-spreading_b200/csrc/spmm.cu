@@ -30,8 +30,8 @@ constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr int kMaxPeers = 8;
 
 static int g_spmm_long_row = 0;  // override of the per-call warp-per-row threshold (lgc_spmm_long_row); 0 = none
+static int g_coop_ctas_per_sm = 2;  // resident CTAs per SM of the cooperative K-layer kernel (lgc_coop_config)
 static int g_spmm_unroll = 0;  // gathers in flight per lane for DIM=64; 0 = choose by grid size (lgc_spmm_config)
-static int g_spmm_hot = 0;     // 1: colidx carries the hot-row flag in bit 31 (lgc_spmm_hot_mode), DIM = 64 only
 
 struct PeerPtrs {
   float* y[kMaxPeers];
@@ -40,26 +40,12 @@ struct PeerPtrs {
 __device__ __forceinline__ float4 ld_row4(const float* p) {
   return __ldg(reinterpret_cast<const float4*>(p));
 }
-// Gathers with an L1 policy chosen per source row (HOT mode): rows of the few hundred highest-degree nodes — a fifth of all
-// gathers under the Zipf-like item popularity — are kept in L1 (evict-last), all other rows bypass it (no-allocate), so
-// the hot set is not flushed by the 80 % of gathers that are never re-referenced soon.  Bit 31 of colidx marks a hot row.
-__device__ __forceinline__ float4 ld_row4_hot(const float* p) {
-  float4 v;
-  asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ float4 ld_row4_cold(const float* p) {
-  float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-  return v;
-}
-
 // Sum of val[e] * X[colidx[e], :] over e in [start, end) for one warp.  On return every
 // lane li of every sub-group holds the full sum for columns [4*li, 4*li+4).
 // UN independent 128-bit gathers are in flight per lane, and the (colidx, val) metadata of the
 // next 32 non-zeros is requested before the gathers of the current 32 are issued, so the
 // dependent metadata -> gather chain is overlapped.
-template <int DIM, int UN, bool HOT = false>
+template <int DIM, int UN>
 __device__ __forceinline__ float4 warp_gather_sum(const int32_t* __restrict__ colidx,
                                                   const float* __restrict__ val,
                                                   const float* __restrict__ X, int start, int end,
@@ -88,20 +74,11 @@ __device__ __forceinline__ float4 warp_gather_sum(const int32_t* __restrict__ co
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
         const int jj = j + u * SUB + sub;
-        int cc = __shfl_sync(0xffffffffu, c, jj & 31);
+        const int cc = __shfl_sync(0xffffffffu, c, jj & 31);
         const float vv = __shfl_sync(0xffffffffu, v, jj & 31);
         const bool ok = jj < n;
         w[u] = ok ? vv : 0.f;
-        if (HOT) {
-          const bool hot = cc < 0;
-          cc &= 0x7fffffff;
-          const float* src = X + (size_t)cc * DIM + li * 4;
-          x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok && hot) x[u] = ld_row4_hot(src);
-          if (ok && !hot) x[u] = ld_row4_cold(src);
-        } else {
-          x[u] = ok ? ld_row4(X + (size_t)cc * DIM + li * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        x[u] = ok ? ld_row4(X + (size_t)cc * DIM + li * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
@@ -135,7 +112,7 @@ __device__ __forceinline__ void store_row4(float* Y, const PeerPtrs& peers, size
   }
 }
 
-template <int DIM, int NPEER, int UN, bool HOT = false>
+template <int DIM, int NPEER, int UN>
 __global__ void __launch_bounds__(kThreads)
 spmm_layer_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                   const float* __restrict__ val, const int32_t* __restrict__ chunk_row,
@@ -157,7 +134,7 @@ spmm_layer_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
     const int row = row_order ? __ldg(row_order + (slot - row_begin)) : slot;
     const int start = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
     if (end - start > long_row) return;  // handled by the chunk CTAs
-    float4 acc = warp_gather_sum<DIM, UN, HOT>(colidx, val, X, start, end, lane);
+    float4 acc = warp_gather_sum<DIM, UN>(colidx, val, X, start, end, lane);
     if (lane < LPR) {
       const size_t off = (size_t)row * DIM + lane * 4;
       if (beta != 0.f) {
@@ -184,7 +161,7 @@ spmm_layer_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
   const int cend = min(cstart + LGC_CHUNK, rend);
   constexpr int PER_WARP = LGC_CHUNK / kWarpsPerBlock;
   const int wstart = min(cstart + warp * PER_WARP, cend), wend = min(wstart + PER_WARP, cend);
-  float4 acc = warp_gather_sum<DIM, UN, HOT>(colidx, val, X, wstart, wend, lane);
+  float4 acc = warp_gather_sum<DIM, UN>(colidx, val, X, wstart, wend, lane);
   if (lane < LPR) *reinterpret_cast<float4*>(&s_part[warp][lane * 4]) = acc;
   __syncthreads();
   const int nch = (rend - rstart + LGC_CHUNK - 1) / LGC_CHUNK;
@@ -350,9 +327,16 @@ propagate_coop_kernel(const CoopParams p) {
         if (lane < LPR) {
           const int row = __ldg(p.split_row + s), first = __ldg(p.split_first + s), cnt = __ldg(p.split_count + s);
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int c = 0; c < cnt; ++c) {
-            const float4 q = __ldcg(reinterpret_cast<const float4*>(p.partial + (size_t)(first + c) * DIM + lane * 4));
-            acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+          // partials are added in slot order (deterministic); eight loads are in flight at a time so that a row cut into
+          // dozens of pieces does not pay one L2 round trip per piece
+          for (int c0 = 0; c0 < cnt; c0 += 8) {
+            float4 q[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              q[j] = c0 + j < cnt ? __ldcg(reinterpret_cast<const float4*>(p.partial + (size_t)(first + c0 + j) * DIM + lane * 4))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { acc.x += q[j].x; acc.y += q[j].y; acc.z += q[j].z; acc.w += q[j].w; }
           }
           const size_t off = (size_t)row * DIM + lane * 4;
           const float4 x0 = ld_row4(p.X0 + off);
@@ -399,17 +383,7 @@ static int launch_spmm(const int32_t* rowptr, const int32_t* colidx, const float
         // (32 regs, 64 warps/SM) beats per-warp ILP; with a single wave the deeper unroll wins
         int un = g_spmm_unroll;
         if (un == 0) un = grid > (int64_t)num_sms() * 8 * 2 ? 2 : 4;
-        if (g_spmm_hot) {
-          if (un == 2) {
-            spmm_layer_kernel<64, NPEER, 2, true><<<(unsigned)grid, kThreads, 0, stream>>>(
-                rowptr, colidx, val, chunk_row, chunk_start, row_chunk_base, chunk_begin, n_chunk_blocks, (int)row_begin,
-                (int)row_end, row_order, X, X0, alpha, beta, Y, peers, partial, counters, long_row);
-          } else {
-            spmm_layer_kernel<64, NPEER, 4, true><<<(unsigned)grid, kThreads, 0, stream>>>(
-                rowptr, colidx, val, chunk_row, chunk_start, row_chunk_base, chunk_begin, n_chunk_blocks, (int)row_begin,
-                (int)row_end, row_order, X, X0, alpha, beta, Y, peers, partial, counters, long_row);
-          }
-        } else if (un == 8) LGC_SPMM_LAUNCH(64, 8);
+        if (un == 8) LGC_SPMM_LAUNCH(64, 8);
         else if (un == 2) LGC_SPMM_LAUNCH(64, 2);
         else LGC_SPMM_LAUNCH(64, 4);
       }
@@ -448,8 +422,9 @@ extern "C" int lgc_spmm_config(int32_t unroll) {
   return LGC_OK;
 }
 
-extern "C" int lgc_spmm_hot_mode(int32_t on) {
-  g_spmm_hot = on ? 1 : 0;
+extern "C" int lgc_coop_config(int32_t ctas_per_sm) {
+  LGC_REQUIRE(ctas_per_sm >= 1 && ctas_per_sm <= 8, "coop config: 1..8 CTAs per SM");
+  g_coop_ctas_per_sm = ctas_per_sm;
   return LGC_OK;
 }
 
@@ -586,7 +561,7 @@ extern "C" int lgc_propagate_mean_coop(const int32_t* rowptr, const int32_t* col
   int per_sm = 0;
   LGC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0));
   if (per_sm < 1) LGC_FAIL(LGC_ERR_CUDA, "propagate coop: kernel does not fit an SM");
-  int64_t grid = (int64_t)num_sms() * (per_sm > 4 ? 4 : per_sm);
+  int64_t grid = (int64_t)num_sms() * (per_sm > g_coop_ctas_per_sm ? g_coop_ctas_per_sm : per_sm);
   const int64_t want = ceil_div(n_units, kWarpsPerBlock);
   if (grid > want) grid = want;
   void* args[] = {(void*)&p};

@@ -26,6 +26,10 @@ _SIGS = {
     "lgc_csr_max_chunks": (_i64, [_i64]),
     "lgc_csr_build_workspace_bytes": (C.c_int, [_i64, _i64, C.POINTER(_sz)]),
     "lgc_csr_build": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, C.POINTER(_i32), _p, _sz, _p]),
+    "lgc_seen_csr_workspace_bytes": (C.c_int, [_i64, C.POINTER(_sz)]),
+    "lgc_seen_csr": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _p, C.POINTER(_i64), _p, _sz, _p]),
+    "lgc_sort_u64_workspace_bytes": (C.c_int, [_i64, C.POINTER(_sz)]),
+    "lgc_sort_u64": (C.c_int, [_p, _p, _i64, _i32, _p, _sz, _p]),
     "lgc_spmm_layer": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i64, _i32, _i64, _i64, _p, _i32, _p, _p, _f32, _f32,
                                  _p, _p, _p, _p]),
     "lgc_spmm_layer_bcast": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i64, _i32, _i64, _i64, _p, _i32, _p, _p, _f32,
@@ -36,7 +40,7 @@ _SIGS = {
     "lgc_zero_rows": (C.c_int, [_p, _p, _i32, _p, _p, _p, _i64, _i64, _p]),
     "lgc_spmm_config": (C.c_int, [_i32]),
     "lgc_spmm_long_row": (C.c_int, [_i32]),
-    "lgc_spmm_hot_mode": (C.c_int, [_i32]),
+    "lgc_coop_config": (C.c_int, [_i32]),
     "lgc_propagate_mean": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i64, _i32, _i32, _p, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "lgc_propagate_mean_coop": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _i32, _i64, _i32, _i32, _p, _p, _p, _p, _p,
                                           _p]),

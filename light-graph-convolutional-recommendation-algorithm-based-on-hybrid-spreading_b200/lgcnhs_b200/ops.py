@@ -128,7 +128,13 @@ class NormGraph:
         o = self._orders.get(key)
         if o is None:
             rp = self.rowptr[row_begin: row_end + 1].to(torch.int64)
-            o = (torch.argsort(rp[1:] - rp[:-1], descending=True, stable=True) + row_begin).to(torch.int32)
+            deg = rp[1:] - rp[:-1]
+            # longest first, equal lengths by ascending row: one stable sort of (max_deg - deg) << 32 | local row
+            # with the library's own radix sort (lgc_sort_u64)
+            mx = int(deg.max()) if deg.numel() else 0
+            keys = ((mx - deg) << 32) | torch.arange(deg.numel(), device=deg.device, dtype=torch.int64)
+            sort_u64(keys, bits=32 + max(1, mx.bit_length()))
+            o = ((keys & 0xFFFFFFFF) + row_begin).to(torch.int32)
             self._orders[key] = o
             # warp-per-row threshold sized to the launch: a lone warp streams ~40 non-zeros per microsecond, so rows
             # up to ~1e-4 x nnz(launch) hide inside the launch when issued first (tools/spmm_rows_probe.py, B200)
@@ -503,13 +509,38 @@ def metrics_from_sums(sums, n_users: int, k: int) -> dict:
 
 
 def seen_csr(users: torch.Tensor, items: torch.Tensor, n_users: int, n_items: int):
-    """(user, item) pairs -> deduplicated int32 CSR (rowptr, item ids ascending) on device."""
-    key = torch.unique(users.to(torch.int64) * n_items + items.to(torch.int64))
-    u = torch.div(key, n_items, rounding_mode="floor")
-    cnt = torch.bincount(u, minlength=n_users)
-    rowptr = torch.zeros(n_users + 1, dtype=torch.int64, device=users.device)
-    torch.cumsum(cnt, 0, out=rowptr[1:])
-    return rowptr.to(torch.int32), (key - u * n_items).to(torch.int32)
+    """(user, item) pairs -> deduplicated int32 CSR (rowptr, item ids ascending) on device: own radix sort + scan +
+    compaction kernels (lgc_seen_csr), standing in for the reference's Python dict / list loops over the pairs
+    (utils/trans.py:51-80, model/LightGCN/recommend.py:92-111)."""
+    if not users.is_cuda:
+        raise LgcnhsError("seen_csr: expected CUDA tensors (the B200 path has no CPU fallback)")
+    users = users.to(torch.int64).contiguous()
+    items = items.to(torch.int64).contiguous()
+    n = int(users.numel())
+    dev = users.device
+    rowptr = torch.empty(n_users + 1, dtype=torch.int32, device=dev)
+    idx = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    nb = C.c_size_t(0)
+    check(lib().lgc_seen_csr_workspace_bytes(n, C.byref(nb)), "seen csr workspace")
+    ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+    n_unique = C.c_int64(0)
+    check(lib().lgc_seen_csr(_ptr(users), _ptr(items), n, int(n_users), int(n_items), _ptr(rowptr), _ptr(idx),
+                             C.byref(n_unique), _ptr(ws), nb.value, _stream()), "seen csr")
+    return rowptr, idx[: n_unique.value].clone() if n_unique.value < n else idx[:n]
+
+
+def sort_u64(keys: torch.Tensor, bits: int = 64) -> torch.Tensor:
+    """Stable ascending radix sort of non-negative int64 keys on the device (lgc_sort_u64), in place; returns keys."""
+    keys = _req(keys, torch.int64, "keys")
+    n = int(keys.numel())
+    if n == 0:
+        return keys
+    tmp = torch.empty_like(keys)
+    nb = C.c_size_t(0)
+    check(lib().lgc_sort_u64_workspace_bytes(n, C.byref(nb)), "sort workspace")
+    ws = torch.empty(nb.value, dtype=torch.uint8, device=keys.device)
+    check(lib().lgc_sort_u64(_ptr(keys), _ptr(tmp), n, int(bits), _ptr(ws), nb.value, _stream()), "sort")
+    return keys
 
 
 # --------------------------------------------------------------------------------------------
