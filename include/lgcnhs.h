@@ -247,13 +247,15 @@ int lgc_peer_barrier(const int32_t* local_flags, int32_t* const* peer_flags_host
  * launch-latency bound).  Work units of <= 128 non-zeros: unit u covers non-zeros [unit_start[u], unit_end[u]) of row
  * unit_row[u]; unit_slot[u] = -1 for a whole row, else the partial-sum slot of a piece of a long row; split_* list the
  * long rows with their first slot and number of pieces (combined in order: deterministic).  partial: n_partials * dim
- * floats.  Same result as lgc_propagate_mean up to fp32 summation order. */
+ * floats; barrier_state: 2 uint32 zeroed once by the caller (grid-barrier counters, left at zero by every launch).
+ * Same result as lgc_propagate_mean up to fp32 summation order. */
 int lgc_propagate_mean_coop(const int32_t* rowptr, const int32_t* colidx, const float* val,
                             const int32_t* unit_row, const int32_t* unit_start, const int32_t* unit_end,
                             const int32_t* unit_slot, int32_t n_units, const int32_t* split_row,
                             const int32_t* split_first, const int32_t* split_count, int32_t n_split,
                             int64_t n_nodes, int32_t dim, int32_t n_layers, const float* X0, float* E,
-                            float* tmp0, float* tmp1, float* partial, lgc_stream_t stream);
+                            float* tmp0, float* tmp1, float* partial, uint32_t* barrier_state,
+                            lgc_stream_t stream);
 
 /* Same barrier with the epoch counter in device memory (the kernel increments *epoch_counter_dev and uses the new
  * value): capturable in a CUDA graph, replayable — all ranks must issue the same sequence of barriers. */

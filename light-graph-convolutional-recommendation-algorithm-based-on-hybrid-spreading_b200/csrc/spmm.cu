@@ -290,13 +290,32 @@ struct CoopParams {
   float* buf1;
   float* E;
   float* partial;             // [n_partials][DIM]
+  unsigned int* barrier;      // [2] arrival counter of the grid barrier + exit counter, zero between launches
 };
+
+// Grid barrier of the cooperative kernel: one arrival counter that only grows during a launch (barrier b completes when
+// it reaches (b + 1) * gridDim.x); the last CTA to leave the kernel resets it, so every launch starts from zero and the
+// launch can be replayed from a CUDA graph.  Thread 0 of every CTA arrives with a release and spins with acquire loads;
+// co-residency of the whole grid is guaranteed by cudaLaunchCooperativeKernel.
+__device__ __forceinline__ void coop_grid_barrier(unsigned int* counter, unsigned int& epoch) {
+  __syncthreads();
+  ++epoch;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const unsigned int target = epoch * gridDim.x;
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while (v < target);
+  }
+  __syncthreads();
+}
 
 template <int DIM>
 __global__ void __launch_bounds__(kThreads)
 propagate_coop_kernel(const CoopParams p) {
-  namespace cg = cooperative_groups;
-  cg::grid_group grid = cg::this_grid();
+  unsigned int epoch = 0;
   constexpr int LPR = DIM / 4;
   const int lane = threadIdx.x & 31;
   const int gwarp = (int)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -322,7 +341,7 @@ propagate_coop_kernel(const CoopParams p) {
       }
     }
     if (p.n_split > 0) {
-      grid.sync();
+      coop_grid_barrier(p.barrier, epoch);
       for (int s = gwarp; s < p.n_split; s += n_warps) {
         if (lane < LPR) {
           const int row = __ldg(p.split_row + s), first = __ldg(p.split_first + s), cnt = __ldg(p.split_count + s);
@@ -346,8 +365,15 @@ propagate_coop_kernel(const CoopParams p) {
         }
       }
     }
-    if (!last) grid.sync();
+    if (!last) coop_grid_barrier(p.barrier, epoch);
     cur = out;
+  }
+  // every CTA that gets here has passed the last barrier: the last one to leave puts the counters back to zero
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(p.barrier + 1, 1u) == gridDim.x - 1) {
+    p.barrier[0] = 0u;
+    p.barrier[1] = 0u;
+    __threadfence();
   }
 }
 
@@ -548,14 +574,16 @@ extern "C" int lgc_propagate_mean_coop(const int32_t* rowptr, const int32_t* col
                                        const int32_t* unit_slot, int32_t n_units, const int32_t* split_row,
                                        const int32_t* split_first, const int32_t* split_count, int32_t n_split,
                                        int64_t n_nodes, int32_t dim, int32_t n_layers, const float* X0, float* E,
-                                       float* tmp0, float* tmp1, float* partial, lgc_stream_t stream) {
+                                       float* tmp0, float* tmp1, float* partial, uint32_t* barrier_state,
+                                       lgc_stream_t stream) {
   LGC_REQUIRE(rowptr && colidx && val && unit_row && unit_start && unit_end && unit_slot && X0 && E, "propagate coop: null pointer");
   LGC_REQUIRE(n_units > 0 && n_layers >= 1 && n_nodes > 0, "propagate coop: empty problem");
   LGC_REQUIRE(n_split == 0 || (split_row && split_first && split_count && partial), "propagate coop: split lists missing");
   LGC_REQUIRE(n_layers == 1 || (tmp0 && (n_layers == 2 || tmp1)), "propagate coop: scratch buffers missing");
   LGC_REQUIRE(dim == 32 || dim == 64 || dim == 128, "propagate coop: embedding dim not in {32,64,128}");
+  LGC_REQUIRE(barrier_state, "propagate coop: barrier state missing");
   CoopParams p{rowptr, colidx, val, unit_row, unit_start, unit_end, unit_slot, split_row, split_first, split_count,
-               n_units, n_split, n_layers, X0, tmp0, tmp1, E, partial};
+               n_units, n_split, n_layers, X0, tmp0, tmp1, E, partial, barrier_state};
   void* fn = dim == 32 ? (void*)propagate_coop_kernel<32> : dim == 64 ? (void*)propagate_coop_kernel<64>
                                                                       : (void*)propagate_coop_kernel<128>;
   int per_sm = 0;

@@ -43,7 +43,7 @@ _SIGS = {
     "lgc_coop_config": (C.c_int, [_i32]),
     "lgc_propagate_mean": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i64, _i32, _i32, _p, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "lgc_propagate_mean_coop": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _i32, _i64, _i32, _i32, _p, _p, _p, _p, _p,
-                                          _p]),
+                                          _p, _p]),
     "lgc_bpr_scratch_floats": (_i64, [_i64]),
     "lgc_bpr_fwd_bwd": (C.c_int, [_p, _p, _i64, _i64, _i32, _p, _p, _p, _i64, _f32, _f32, _p, _p, _p, _p, _p]),
     "lgc_bpr_det_workspace_bytes": (_i64, [_i64, _i32]),

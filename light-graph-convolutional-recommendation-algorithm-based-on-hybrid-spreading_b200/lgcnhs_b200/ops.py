@@ -229,14 +229,15 @@ class NormGraph:
                           "split_first": i32(split_first) if n_split else None,
                           "split_count": i32(split_pieces) if n_split else None,
                           "n_units": int(unit_row.numel()), "n_split": n_split, "n_partials": int(split_pieces.sum()) if n_split else 0,
-                          "partial": {}}
+                          "partial": {}, "barrier": torch.zeros(2, dtype=torch.int32, device=dev)}
         return self._coop
 
     def propagate_mean(self, X0: torch.Tensor, n_layers: int, out: Optional[torch.Tensor] = None,
                        tmp: Optional[tuple[torch.Tensor, torch.Tensor]] = None, coop: Optional[bool] = None) -> torch.Tensor:
         """E = mean_l(A_hat^l X0), l = 0..n_layers (model/LightGCN/model.py:56-69).
-        coop (default: graphs with <= COOP_MAX_NNZ non-zeros, LGCNHS_NO_COOP=1 disables): all layers in ONE cooperative
-        launch with grid barriers between them (small graphs are launch-latency bound)."""
+        coop=True (or LGCNHS_COOP=1 for graphs with <= COOP_MAX_NNZ non-zeros): all layers in ONE cooperative launch with
+        grid barriers between them.  Opt-in: measured on B200 (tools/coop_probe.py, profiles/r2_coop_probe.txt) the grid
+        barriers cost more than the launches they replace at every configured shape."""
         X0 = _req(X0, torch.float32, "X0")
         n, dim = self.n_nodes, int(X0.shape[1])
         if X0.shape[0] != n:
@@ -246,7 +247,7 @@ class NormGraph:
         if tmp is None:
             tmp = (torch.empty_like(X0), torch.empty_like(X0))
         if coop is None:
-            coop = 0 < self.nnz <= self.COOP_MAX_NNZ and n_layers >= 1 and os.environ.get("LGCNHS_NO_COOP", "0") != "1"
+            coop = 0 < self.nnz <= self.COOP_MAX_NNZ and n_layers >= 1 and os.environ.get("LGCNHS_COOP", "0") == "1"
         if coop:
             cu = self.coop_units()
             part = cu["partial"].get(dim)
@@ -256,7 +257,8 @@ class NormGraph:
                                                 _ptr(cu["start"]), _ptr(cu["end"]), _ptr(cu["slot"]), cu["n_units"],
                                                 _ptr(cu["split_row"]), _ptr(cu["split_first"]), _ptr(cu["split_count"]),
                                                 cu["n_split"], n, dim, int(n_layers), _ptr(X0), _ptr(out), _ptr(tmp[0]),
-                                                _ptr(tmp[1]), _ptr(part), _stream()), "propagate_mean (cooperative)")
+                                                _ptr(tmp[1]), _ptr(part), _ptr(cu["barrier"]), _stream()),
+                  "propagate_mean (cooperative)")
             return out
         partial, counters = self._scr(dim)
         check(lib().lgc_propagate_mean(_ptr(self.rowptr), _ptr(self.colidx), _ptr(self.val), _ptr(self.chunk_row),

@@ -122,8 +122,11 @@ def test_bpr_deterministic_scatter(dev, U, M, D, B):
     assert abs((out[0] - out[1]).item() - reg_ref) <= 2e-5 * abs(reg_ref) + 1e-6
     cnt = (torch.bincount(users, minlength=U + M) + torch.bincount(U + pos, minlength=U + M)
            + torch.bincount(U + neg, minlength=U + M)).double()[:, None]
-    assert_close(gE, Er.grad, "det dL/dE", sum_abs=cnt * 2 * float(E.abs().max()) / B)
-    assert_close(gX0, X0r.grad, "det dL/dX0", sum_abs=cnt * 2 * eps * float(X0.abs().max()))
+    # duplicates are added SEQUENTIALLY in fp32 (up to ~800 same-sign regulariser terms per row in the last case): the
+    # admissible difference between two fp32 summation orders grows with the number of terms
+    n_ops = max(8, int(cnt.max()) // 4)
+    assert_close(gE, Er.grad, "det dL/dE", sum_abs=cnt * 2 * float(E.abs().max()) / B, n_ops=n_ops)
+    assert_close(gX0, X0r.grad, "det dL/dX0", sum_abs=cnt * 2 * eps * float(X0.abs().max()), n_ops=n_ops)
     untouched = cnt[:, 0] == 0
     assert float(gE[untouched.to(dev)].abs().max() if untouched.any() else 0.0) == 0.0
 
