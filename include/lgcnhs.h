@@ -469,6 +469,18 @@ int64_t lgc_probe_gather_threads(void);
 int lgc_probe_gather(const float* table, int64_t n_rows, int32_t dim, int64_t n_gathers,
                      uint32_t seed, float* out, int64_t* gathers_done_host, lgc_stream_t stream);
 
+/* lgc_spmm_layer over an explicit LIST of rows (device int32[n_rows], any subset of the nodes; longest rows first gives
+ * the best balance) plus up to two ranges of the long-row chunk list, in ONE launch; every finished row is stored into
+ * n_peers replicas (n_peers = 1 with the local buffer: a plain local SpMM).  The multi-GPU partition gives a rank a slice
+ * of the user rows and a slice of the item rows: one mixed launch keeps both row classes in flight together. */
+int lgc_spmm_rows_bcast(const int32_t* rowptr, const int32_t* colidx, const float* val,
+                        const int32_t* chunk_row, const int32_t* chunk_start,
+                        const int32_t* row_chunk_base, int32_t chunk_begin, int32_t chunk_end,
+                        int32_t chunk_begin2, int32_t chunk_end2, int64_t n_nodes, int32_t dim,
+                        const int32_t* row_list, int64_t n_rows, int32_t long_row, const float* X,
+                        const float* X0, float alpha, float beta, float* const* peer_Y_host,
+                        int32_t n_peers, float* partial, int32_t* counters, lgc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

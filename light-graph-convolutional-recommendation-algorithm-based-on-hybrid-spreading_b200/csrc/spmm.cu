@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kThreads)
 spmm_layer_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                   const float* __restrict__ val, const int32_t* __restrict__ chunk_row,
                   const int32_t* __restrict__ chunk_start, const int32_t* __restrict__ row_chunk_base,
-                  int chunk_begin, int n_chunk_blocks, int row_begin, int row_end,
+                  int chunk_begin, int n_chunk_blocks, int chunk_begin2, int n_chunk_blocks1, int row_begin, int row_end,
                   const int32_t* __restrict__ row_order,
                   const float* __restrict__ X, const float* __restrict__ X0, float alpha, float beta,
                   float* __restrict__ Y, PeerPtrs peers, float* __restrict__ partial,
@@ -153,7 +153,9 @@ spmm_layer_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
   // ---------------- long rows: one CTA per LGC_CHUNK non-zeros ----------------
   __shared__ float s_part[kWarpsPerBlock][DIM];
   __shared__ int s_last;
-  const int chunk = chunk_begin + (int)blockIdx.x;
+  // the chunk CTAs cover up to two ranges of the chunk list (a rank's user rows and item rows in ONE launch)
+  const int chunk = (int)blockIdx.x < n_chunk_blocks1 ? chunk_begin + (int)blockIdx.x
+                                                      : chunk_begin2 + ((int)blockIdx.x - n_chunk_blocks1);
   const int row = __ldg(chunk_row + chunk);
   const int cstart = __ldg(chunk_start + chunk);
   const int rstart = __ldg(rowptr + row), rend = __ldg(rowptr + row + 1);
@@ -383,15 +385,17 @@ static int launch_spmm(const int32_t* rowptr, const int32_t* colidx, const float
                        const int32_t* row_chunk_base, int chunk_begin, int chunk_end,
                        int64_t row_begin, int64_t row_end, const int32_t* row_order, int long_row_arg, int dim,
                        const float* X, const float* X0, float alpha, float beta, float* Y, const PeerPtrs& peers,
-                       float* partial, int32_t* counters, cudaStream_t stream) {
-  const int n_chunk_blocks = chunk_end - chunk_begin;
+                       float* partial, int32_t* counters, cudaStream_t stream, int chunk_begin2 = 0, int chunk_end2 = 0) {
+  const int n_chunk_blocks1 = chunk_end - chunk_begin;
+  const int n_chunk_blocks = n_chunk_blocks1 + (chunk_end2 - chunk_begin2);
   const int64_t n_rows = row_end - row_begin;
   const int64_t grid = n_chunk_blocks + ceil_div(n_rows, kWarpsPerBlock);
   if (grid == 0) return LGC_OK;
 #define LGC_SPMM_LAUNCH(D, UNR)                                                                   \
   spmm_layer_kernel<D, NPEER, UNR><<<(unsigned)grid, kThreads, 0, stream>>>(                      \
       rowptr, colidx, val, chunk_row, chunk_start, row_chunk_base, chunk_begin, n_chunk_blocks,   \
-      (int)row_begin, (int)row_end, row_order, X, X0, alpha, beta, Y, peers, partial, counters, long_row)
+      chunk_begin2, n_chunk_blocks1, (int)row_begin, (int)row_end, row_order, X, X0, alpha, beta, Y, peers, partial, \
+      counters, long_row)
   // Rows of LGC_LONG_ROW < nnz <= long_row take the warp-per-row path in this launch: it is cheaper than chunk
   // partials + ticket + re-read (ML-20M layer: 680 -> 525 us at long_row 1024), but a lone warp streams only ~40
   // non-zeros per microsecond, so only launches with enough work hide such rows, and they must be issued first
@@ -506,6 +510,44 @@ extern "C" int lgc_spmm_layer_bcast(const int32_t* rowptr, const int32_t* colidx
     LGC_BCAST(5); LGC_BCAST(6); LGC_BCAST(7); LGC_BCAST(8);
   }
 #undef LGC_BCAST
+  return LGC_ERR_INVALID;
+}
+
+// One launch over an explicit LIST of rows (device int32, any subset of the nodes, longest first for best balance) and up
+// to two ranges of the chunk list; every finished row is stored into n_peers replicas (n_peers = 1 with the local
+// buffer = plain local SpMM).  Used by the multi-GPU partition, where a rank owns a slice of the user rows AND a slice of
+// the item rows: one mixed launch keeps the short user rows and the chunked hub rows of the items in flight together,
+// which two back-to-back launches do not (measured: 61 / 44 Gnnz/s apart, 63 mixed).
+extern "C" int lgc_spmm_rows_bcast(const int32_t* rowptr, const int32_t* colidx, const float* val,
+                                   const int32_t* chunk_row, const int32_t* chunk_start, const int32_t* row_chunk_base,
+                                   int32_t chunk_begin, int32_t chunk_end, int32_t chunk_begin2, int32_t chunk_end2,
+                                   int64_t n_nodes, int32_t dim, const int32_t* row_list, int64_t n_rows, int32_t long_row,
+                                   const float* X, const float* X0, float alpha, float beta, float* const* peer_Y_host,
+                                   int32_t n_peers, float* partial, int32_t* counters, lgc_stream_t stream) {
+  int rc = check_spmm_args(rowptr, colidx, val, chunk_row, chunk_start, row_chunk_base, chunk_begin, chunk_end, n_nodes, 0,
+                           n_rows, X, X0, beta, partial, counters);
+  if (rc) return rc;
+  LGC_REQUIRE(row_list && n_rows >= 0 && n_rows <= n_nodes, "spmm rows: row list missing / too long");
+  LGC_REQUIRE(0 <= chunk_begin2 && chunk_begin2 <= chunk_end2, "spmm rows: bad second chunk range");
+  LGC_REQUIRE(chunk_end2 == chunk_begin2 || (chunk_row && chunk_start && row_chunk_base && partial && counters),
+              "spmm rows: chunk list given without chunk arrays / scratch");
+  LGC_REQUIRE(peer_Y_host && n_peers >= 1 && n_peers <= kMaxPeers, "spmm rows: 1..8 replicas");
+  PeerPtrs peers{};
+  for (int p = 0; p < n_peers; ++p) {
+    LGC_REQUIRE(peer_Y_host[p] && ((uintptr_t)peer_Y_host[p] & 15) == 0, "spmm rows: bad replica pointer");
+    peers.y[p] = peer_Y_host[p];
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+#define LGC_ROWS(NP)                                                                                              \
+  case NP:                                                                                                        \
+    return launch_spmm<NP>(rowptr, colidx, val, chunk_row, chunk_start, row_chunk_base, chunk_begin, chunk_end, 0, \
+                           n_rows, row_list, long_row, dim, X, X0, alpha, beta, nullptr, peers, partial, counters, s, \
+                           chunk_begin2, chunk_end2)
+  switch (n_peers) {
+    LGC_ROWS(1); LGC_ROWS(2); LGC_ROWS(3); LGC_ROWS(4);
+    LGC_ROWS(5); LGC_ROWS(6); LGC_ROWS(7); LGC_ROWS(8);
+  }
+#undef LGC_ROWS
   return LGC_ERR_INVALID;
 }
 

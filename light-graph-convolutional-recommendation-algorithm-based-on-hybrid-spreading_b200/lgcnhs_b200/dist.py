@@ -153,8 +153,8 @@ class RowPartitionedPropagation:
             oi = res if last else (l & 1)
             alpha = 1.0 / (layers + 1) if last else 1.0
             if self.mode == "p2p":
-                for a, b, ch in self.my_parts:
-                    g.spmm_bcast(cur, x0, alpha, 1.0, self.peer_ptrs[oi], a, b, ch)
+                # ONE mixed launch over this rank's user rows and item rows (longest first across both)
+                g.spmm_rows_bcast(cur, x0, alpha, 1.0, self.peer_ptrs[oi], [(a, b) for a, b, _ in self.my_parts])
                 self.peer_barrier()
             elif self.mode == "p2p-nccl":
                 for a, b, ch in self.my_parts:

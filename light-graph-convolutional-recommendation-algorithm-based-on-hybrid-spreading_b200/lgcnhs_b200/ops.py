@@ -79,6 +79,7 @@ class NormGraph:
         self.chunk_row = self.chunk_row[: max(self.n_chunks, 1)].clone()
         self.chunk_start = self.chunk_start[: max(self.n_chunks, 1)].clone()
         self._coop = None
+        self._lists: dict = {}
         self._scratch: dict[int, tuple[torch.Tensor, torch.Tensor]] = {}
         self._orders: dict[tuple[int, int], torch.Tensor] = {}
         self._long_rows: dict[tuple[int, int], int] = {}
@@ -115,7 +116,7 @@ class NormGraph:
         t.chunk_row = crow.to(torch.int32) if t.n_chunks else torch.zeros(1, dtype=torch.int32, device=dev)
         t.chunk_start = ((rowptr[:-1][crow] + within * CHUNK).to(torch.int32) if t.n_chunks
                          else torch.zeros(1, dtype=torch.int32, device=dev))
-        t._scratch, t._orders, t._long_rows, t._coop = {}, {}, {}, None
+        t._scratch, t._orders, t._long_rows, t._coop, t._lists = {}, {}, {}, None, {}
         t.use_row_order = self.use_row_order
         return t
 
@@ -231,6 +232,43 @@ class NormGraph:
                           "n_units": int(unit_row.numel()), "n_split": n_split, "n_partials": int(split_pieces.sum()) if n_split else 0,
                           "partial": {}, "barrier": torch.zeros(2, dtype=torch.int32, device=dev)}
         return self._coop
+
+    def row_list(self, ranges: Sequence[tuple[int, int]]):
+        """(rows of the given ranges longest first as one int32 list, warp-per-row threshold of a launch over them, up to
+        two chunk ranges) for lgc_spmm_rows_bcast; cached per set of ranges."""
+        key = tuple((int(a), int(b)) for a, b in ranges if b > a)
+        hit = self._lists.get(key)
+        if hit is None:
+            rp = self.rowptr.to(torch.int64)
+            rows = torch.cat([torch.arange(a, b, device=self.device, dtype=torch.int64) for a, b in key])
+            deg = rp[rows + 1] - rp[rows]
+            mx = int(deg.max()) if deg.numel() else 0
+            keys = ((mx - deg) << 32) | rows
+            sort_u64(keys, bits=32 + max(1, mx.bit_length()))
+            nnz = int(deg.sum())
+            t = 2 ** int(round(math.log2(max(1.0, nnz * 1e-4))))
+            chunks = [self.chunk_range(a, b) for a, b in key][:2]
+            while len(chunks) < 2:
+                chunks.append((0, 0))
+            if len(key) > 2:
+                raise LgcnhsError("row_list: at most two row ranges per launch")
+            hit = ((keys & 0xFFFFFFFF).to(torch.int32), int(min(2048, max(LONG_ROW, t))), chunks)
+            self._lists[key] = hit
+        return hit
+
+    def spmm_rows_bcast(self, X: torch.Tensor, X0: Optional[torch.Tensor], alpha: float, beta: float,
+                        peer_ptrs: Sequence[int], ranges: Sequence[tuple[int, int]]) -> None:
+        """One mixed launch over up to two row ranges, every finished row stored into all replicas."""
+        X = _req(X, torch.float32, "X")
+        n, dim = self.n_nodes, int(X.shape[1])
+        rows, long_row, ch = self.row_list(ranges)
+        partial, counters = self._scr(dim)
+        arr = (C.c_void_p * len(peer_ptrs))(*[C.c_void_p(p) for p in peer_ptrs])
+        check(lib().lgc_spmm_rows_bcast(_ptr(self.rowptr), _ptr(self.colidx), _ptr(self.val), _ptr(self.chunk_row),
+                                        _ptr(self.chunk_start), _ptr(self.row_chunk_base), ch[0][0], ch[0][1], ch[1][0],
+                                        ch[1][1], n, dim, _ptr(rows), int(rows.numel()), long_row, _ptr(X), _ptr(X0),
+                                        float(alpha), float(beta), arr, len(peer_ptrs), _ptr(partial), _ptr(counters),
+                                        _stream()), "spmm rows bcast")
 
     def propagate_mean(self, X0: torch.Tensor, n_layers: int, out: Optional[torch.Tensor] = None,
                        tmp: Optional[tuple[torch.Tensor, torch.Tensor]] = None, coop: Optional[bool] = None) -> torch.Tensor:

@@ -45,17 +45,25 @@ for split in (None, d.n_users):
         for a, b, ch in prop.my_parts:
             g.spmm_bcast(x0, x0, 1.0, 1.0, prop.peer_ptrs[0], a, b, ch)
 
+    def mixed_stores():
+        g.spmm_rows_bcast(x0, x0, 1.0, 1.0, prop.peer_ptrs[0], [(a, b) for a, b, _ in prop.my_parts])
+
     def with_barrier():
         with_stores()
         prop.peer_barrier()
 
+    dist.barrier()
     t_local = timed(local_only)
+    dist.barrier()
     t_store = timed(with_stores)
+    dist.barrier()
+    t_mixed = timed(mixed_stores)
     t_bar = timed(with_barrier)
     t_full = timed(lambda: prop.propagate_mean(x0, 3), reps=5) / 3
     nnz = sum(int(g.rowptr[b]) - int(g.rowptr[a]) for a, b, _ in prop.my_parts)
     print(f"rank {rank}/{world} split={'users/items' if split else 'single'} parts={[(a, b) for a, b, _ in prop.my_parts]} "
-          f"nnz={nnz}: local {t_local:.1f} us ({nnz / t_local / 1e3:.1f} Gnnz/s) | +peer stores {t_store:.1f} us | "
+          f"nnz={nnz}: local {t_local:.1f} us ({nnz / t_local / 1e3:.1f} Gnnz/s) | +peer stores {t_store:.1f} us | ONE mixed launch "
+          f"{t_mixed:.1f} us | "
           f"+barrier {t_bar:.1f} us | full layer {t_full:.1f} us", flush=True)
     dist.barrier()
     del prop
