@@ -699,7 +699,7 @@ def main():
     ap.add_argument("--shape", default="ml-20m")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-spreading", action="store_true")
-    ap.add_argument("--split", type=int, default=0, help="multi-GPU: partition user rows and item rows separately (1) or as one range (0)")
+    ap.add_argument("--split", type=int, default=1, help="multi-GPU: partition user rows and item rows separately (1, default: every rank gets the same mix of both row classes, one mixed launch per layer) or as one range (0)")
     ap.add_argument("--mode", default="p2p", choices=["p2p", "p2p-nccl", "nccl"], help="multi-GPU layer exchange")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

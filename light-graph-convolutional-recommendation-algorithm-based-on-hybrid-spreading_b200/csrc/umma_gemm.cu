@@ -312,8 +312,15 @@ constexpr int kPStageBytes = kAStage + kPBStage;
 static_assert((size_t)kPStages * kPStageBytes <= (size_t)kStages * kStageBytes, "pair pipeline must fit the same smem budget");
 
 // EPI 0: store C (optionally mirrored, schedule 1);  EPI 1: fused row-wise top-k (schedule 2), C is never written.
+// EPI 1 runs EIGHT epilogue warps (two per scheduler): two threads share an output row, each ranks one half of the
+// tile's columns into its own candidate buffer, and they share the row's pruning threshold through shared memory.
+// With four warps the epilogue was latency-bound (one warp per scheduler, IPC ~0.1, ncu round 2) and the buffer
+// compactions landed on the critical path of a one-wave launch (0.45 ms against 0.21 ms for the plain GEMM at ML-1M).
+constexpr int kEpiParts = 2;
+constexpr int kThreadsTopk = 64 + 32 * 4 * kEpiParts;   // 320
+
 template <int KIND, int PLANES, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EPI == 1 ? kThreadsTopk : kThreads, 1)
 umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                       const __grid_constant__ CUtensorMap tmapBh, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -326,6 +333,7 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
   uint64_t* tfull = bars + 2 * kPStages;       // [2]        per CTA
   uint64_t* tempty = bars + 2 * kPStages + 2;  // [2]        used on the leader
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPStages + 4);
+  uint32_t* s_row_thr = tmem_slot + 4;   // [128] EPI 1: value key of the best known k-th score of each of the CTA's rows
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -333,12 +341,13 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
   constexpr int NB = PLANES == 3 ? 80 : PLANES == 4 ? 64 : 128;  // output columns per tile
   constexpr int n_mma = PLANES * NB;                              // MMA N (both halves)
+  constexpr int kEpiWarps = EPI == 1 ? 4 * kEpiParts : 4;
   constexpr int H = n_mma / 2;                                    // B rows staged by each CTA
   const int n_chunks = (p.num_kb + p.chunk_kb - 1) / p.chunk_kb;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kPStages; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 2 * kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapB) : "memory");
@@ -431,26 +440,42 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
       }
     }
   } else {
-    // ------------------------------ epilogue (warps 2..5, both CTAs) ------------------------------
-    const int q = warp & 3;
+    // ------------------------------ epilogue (warps 2.., both CTAs) ------------------------------
+    const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    const int cpart = EPI == 1 ? (warp - 2) >> 2 : 0;   // EPI 1: which part of the tile's columns this warp ranks
+    const int rloc = q * 32 + lane;                // row inside the CTA's 128
+    constexpr int kGroups = NB / 16;
+    constexpr int kG0 = EPI == 1 ? (kGroups + kEpiParts - 1) / kEpiParts : kGroups;   // groups of 16 columns of part 0
+    const int g_begin = EPI == 1 ? cpart * kG0 : 0;
+    const int g_end = EPI == 1 ? (cpart == kEpiParts - 1 ? kGroups : (cpart + 1) * kG0) : kGroups;
+    constexpr int kPartCols = kG0 * 16;            // most columns one thread can offer per tile
     int it = 0;
-    // fused top-k state of this thread's row (EPI 1): threshold key / value and fill of its candidate buffer
+    // fused top-k state of this thread's (row, column part) (EPI 1): own threshold key and fill of its candidate buffer
     unsigned long long sel_thr = 0ull;
-    float sel_thr_f = -INFINITY;
     int sel_cnt = 0;
     unsigned long long* sel_buf = nullptr;
     TileSched ts{};
     while (sched_next(ts, p, cluster_id, n_clusters)) {
       const int m_blk = ts.m, n_blk = ts.n;
-      const int64_t row = (int64_t)m_blk * 256 + (int64_t)rank * kBlockM + q * 32 + lane;
+      const int64_t row = (int64_t)m_blk * 256 + (int64_t)rank * kBlockM + rloc;
       const bool row_ok = row < p.M;
       const float rscale = (row_ok && p.rs) ? __ldg(p.rs + row) : 1.0f;
       float* crow = (EPI == 0) ? p.C + (row_ok ? row : 0) * p.ldc : nullptr;
       // schedule 1: this tile lies strictly above the diagonal blocks -> its transpose is not computed anywhere else
       const bool mirror = EPI == 0 && p.mode == 1 && (long long)n_blk * NB >= (long long)(m_blk + 1) * 256;
-      if (EPI == 1 && ts.first) {
-        sel_thr = 0ull; sel_thr_f = -INFINITY; sel_cnt = 0;
-        sel_buf = p.cand + ((size_t)(row_ok ? row : 0) * p.segs + ts.seg) * kCandCap;
+      float sel_thr_f = -INFINITY;
+      if (EPI == 1) {
+        if (ts.first) {
+          sel_thr = 0ull; sel_cnt = 0;
+          sel_buf = p.cand + ((size_t)(row_ok ? row : 0) * (p.segs * kEpiParts) + ts.seg * kEpiParts + cpart) * kCandCap;
+          // all epilogue warps of the CTA start a work item together: reset the shared row thresholds
+          asm volatile("bar.sync 1, %0;" ::"r"(32 * kEpiWarps) : "memory");
+          if (cpart == 0) s_row_thr[rloc] = 0u;
+          asm volatile("bar.sync 1, %0;" ::"r"(32 * kEpiWarps) : "memory");
+        }
+        // pruning threshold of this tile: the row's best known k-th score over both column parts
+        const uint32_t tk = s_row_thr[rloc];
+        sel_thr_f = row_ok ? (tk ? key_float(tk) : -INFINITY) : INFINITY;
       }
       // EPI 1: the exclusion bits of this row for the tile's NB columns, fetched BEFORE waiting for the accumulator so
       // that their latency hides behind the tile's MMAs (a dependent global load per surviving value would serialise
@@ -470,7 +495,7 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
 #pragma unroll
         for (int i = 0; i < MW; ++i) mbits[i] = __funnelshift_r(raw[i], raw[i + 1], sh);
       }
-      float run[NB];
+      float run[EPI == 1 ? 1 : NB];
       for (int ch = 0; ch < n_chunks; ++ch, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
@@ -479,7 +504,9 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride;
         const bool first = ch == 0, last = ch == n_chunks - 1;
 #pragma unroll
-        for (int c0 = 0; c0 < NB; c0 += 16) {
+        for (int g = 0; g < kGroups; ++g) {
+          if (EPI == 1 && (g < g_begin || g >= g_end)) continue;
+          const int c0 = g * 16;
           uint32_t r[PLANES][16];
 #pragma unroll
           for (int pl = 0; pl < PLANES; ++pl) tmem_ld16(t_row + pl * NB + c0, r[pl]);
@@ -491,8 +518,10 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
               float a = __uint_as_float(r[PLANES - 1][j]);
 #pragma unroll
               for (int pl = PLANES - 2; pl >= 0; --pl) a += __uint_as_float(r[pl][j]);
-              if (!first) a += run[c0 + j];
-              run[c0 + j] = a;
+              if (EPI == 0) {
+                if (!first) a += run[c0 + j];
+                run[c0 + j] = a;
+              }
               out[j] = a * (float)p.scale;
             } else {
               long long tot = 0;
@@ -529,10 +558,13 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
                 }
               }
             } else {
-              // ---- fused selection: one float compare per value against the row's current k-th best; survivors get
-              //      their exact 64-bit key (value, column), pass the exclusion bit test and are appended to the
-              //      row's private buffer (plain stores: no other thread owns this row) ----
-              if (row_ok) {
+              // ---- fused selection: ONE compare per 16 values (their maximum against the row's threshold); in a group
+              //      with a survivor every value gets its exact 64-bit key (value, column), passes the exclusion bit
+              //      test and is appended to the thread's private buffer (plain stores) ----
+              float mx = fmaxf(fmaxf(fmaxf(out[0], out[1]), fmaxf(out[2], out[3])), fmaxf(fmaxf(out[4], out[5]), fmaxf(out[6], out[7])));
+              mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(out[8], out[9]), fmaxf(out[10], out[11])),
+                                   fmaxf(fmaxf(out[12], out[13]), fmaxf(out[14], out[15]))));
+              if (mx >= sel_thr_f) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                   const int64_t col = col0 + j;
@@ -551,10 +583,10 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
         if (lane == 0) mbar_arrive_leader(&tempty[acc]);   // the accumulator is free: the next tile's MMAs may start
       }
       if (EPI == 1) {
-        // rows whose buffer could overflow during the next tile are compacted now, one row at a time, by the whole
-        // warp (radix select in registers, select.cuh); the TMEM buffer has been released already, so this overlaps
-        // the tensor-core work of the following tiles
-        uint32_t need = __ballot_sync(0xffffffffu, sel_cnt + NB > kCandCap);
+        // buffers that could overflow during the next tile are compacted now, one at a time, by the whole warp (radix
+        // select in registers, select.cuh); the TMEM buffer has been released already, so this overlaps the tensor-core
+        // work of the following tiles.  The new k-th best is published for the row's other column part.
+        uint32_t need = __ballot_sync(0xffffffffu, sel_cnt + kPartCols > kCandCap);
         while (need) {
           const int rl = __ffs(need) - 1;
           need &= need - 1u;
@@ -566,10 +598,10 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
           if (lane == rl) {
             sel_cnt = kept;
             sel_thr = t;
-            sel_thr_f = t ? key_float((uint32_t)(t >> 32)) : -INFINITY;
+            if (t) atomicMax(&s_row_thr[rloc], (uint32_t)(t >> 32));
           }
         }
-        if (ts.last && row_ok) p.cand_cnt[(size_t)row * p.segs + ts.seg] = sel_cnt;
+        if (ts.last && row_ok) p.cand_cnt[(size_t)row * (p.segs * kEpiParts) + ts.seg * kEpiParts + cpart] = sel_cnt;
       }
     }
   }
@@ -678,7 +710,7 @@ static int topk_segments(int64_t M, int64_t N, int planes) {
 }
 
 static size_t topk_scratch_bytes(int64_t M, int64_t N, int planes) {
-  const size_t rows = (size_t)M * topk_segments(M, N, planes);
+  const size_t rows = (size_t)M * topk_segments(M, N, planes) * kEpiParts;
   return align_up(rows * kCandCap * sizeof(unsigned long long), 256) + align_up(rows * sizeof(int), 256);
 }
 
@@ -760,7 +792,7 @@ static int gemm_planes_impl(int32_t kind, const void* A, int64_t lda, const void
     } else if (mode == 2) {
       p.segs = topk_segments(M, N, planes);
       work = (int64_t)p.tiles_m * p.segs;
-      const size_t rows = (size_t)M * p.segs;
+      const size_t rows = (size_t)M * p.segs * kEpiParts;
       LGC_REQUIRE(topk->scratch && topk->scratch_bytes >= topk_scratch_bytes(M, N, planes), "resource_topk: scratch too small");
       LGC_REQUIRE(((uintptr_t)topk->scratch & 255) == 0, "resource_topk: scratch must be 256-byte aligned");
       p.cand = reinterpret_cast<unsigned long long*>(topk->scratch);
@@ -777,10 +809,11 @@ static int gemm_planes_impl(int32_t kind, const void* A, int64_t lda, const void
     static DeviceOnce attr;                                                                                     \
     if (attr.need()) {                                                                                          \
       LGC_CUDA(cudaFuncSetAttribute(umma_gemm_pair_kernel<KD, PL, EP>,                                          \
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));             \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBytes + 512)));     \
       attr.mark();                                                                                              \
     }                                                                                                           \
-    umma_gemm_pair_kernel<KD, PL, EP><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, tmBh, p);               \
+    umma_gemm_pair_kernel<KD, PL, EP><<<grid, EP == 1 ? kThreadsTopk : kThreads, kSmemBytes + 512, stream>>>(   \
+        tmA, tmB, tmBh, p);                                                                                     \
     launched = true;                                                                                            \
   }
     LGC_GEMM_PAIR_CASE(0, 1, 0) LGC_GEMM_PAIR_CASE(0, 2, 0) LGC_GEMM_PAIR_CASE(0, 3, 0)
@@ -791,7 +824,7 @@ static int gemm_planes_impl(int32_t kind, const void* A, int64_t lda, const void
     LGC_LAUNCH_CHECK("umma_gemm_pair_kernel");
     if (mode == 2) {
       topk_merge_kernel<kCandCap><<<(unsigned)ceil_div(M, kMergeWarps), kMergeWarps * 32, 0, stream>>>(
-          p.cand, p.cand_cnt, M, p.segs, topk->k, topk->out_idx, topk->out_val);
+          p.cand, p.cand_cnt, M, p.segs * kEpiParts, topk->k, topk->out_idx, topk->out_val);
       LGC_LAUNCH_CHECK("topk_merge_kernel");
     }
     return LGC_OK;
