@@ -58,6 +58,11 @@ struct GemmParams {
   int k;
   unsigned long long* cand;      // [M * segs][kCandCap] candidate keys
   int* cand_cnt;                 // [M * segs]
+  // ---- multi-GPU (schedule 1): this rank computes every n_ranks-th cluster slot of the symmetric schedule and stores
+  //      each tile (and its mirror) into ALL replicas of C (peer pointers through CUDA IPC): a fused GEMM + all-gather ----
+  float* Cpeer[8];
+  int n_peers;                   // 0: store to C only
+  int rank_slot, n_ranks;        // this rank's offset / the stride of the cluster slots (0 / 1 on one GPU)
 };
 
 
@@ -338,7 +343,9 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  // cluster slot in the (possibly multi-GPU) tile schedule: rank r owns slots r, r + n_ranks, ... of every stride
+  const int cluster_id = (int)(blockIdx.x >> 1) * (p.n_ranks > 0 ? p.n_ranks : 1) + p.rank_slot;
+  const int n_clusters = (int)(gridDim.x >> 1) * (p.n_ranks > 0 ? p.n_ranks : 1);
   constexpr int NB = PLANES == 3 ? 80 : PLANES == 4 ? 64 : 128;  // output columns per tile
   constexpr int n_mma = PLANES * NB;                              // MMA N (both halves)
   constexpr int kEpiWarps = EPI == 1 ? 4 * kEpiParts : 4;
@@ -539,7 +546,7 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
               out[j] = out[j] * rscale * cscale;
             }
             if (EPI == 0) {
-              if (row_ok) {
+              if (row_ok && p.n_peers == 0) {
                 if (col0 + 16 <= p.N && (p.ldc & 3) == 0 && ((uintptr_t)p.C & 15) == 0) {
 #pragma unroll
                   for (int j = 0; j < 16; j += 4)
@@ -555,6 +562,27 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_co
 #pragma unroll
                   for (int j = 0; j < 16; ++j)
                     if (col0 + j < p.N) p.C[(col0 + j) * p.ldc + row] = out[j];
+                }
+              } else if (row_ok) {
+                // multi-GPU: the tile (and its mirror) goes into every rank's replica of C over NVLink
+                const bool vec = col0 + 16 <= p.N && (p.ldc & 3) == 0;
+                for (int pr = 0; pr < p.n_peers; ++pr) {
+                  float* cb = p.Cpeer[pr];
+                  float* cr = cb + row * p.ldc;
+                  if (vec) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                      *reinterpret_cast<float4*>(cr + col0 + j) = make_float4(out[j], out[j + 1], out[j + 2], out[j + 3]);
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                      if (col0 + j < p.N) cr[col0 + j] = out[j];
+                  }
+                  if (mirror) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                      if (col0 + j < p.N) cb[(col0 + j) * p.ldc + row] = out[j];
+                  }
                 }
               }
             } else {
@@ -715,10 +743,15 @@ static size_t topk_scratch_bytes(int64_t M, int64_t N, int planes) {
 }
 
 // mode 0: plain; 1: symmetric output (kind 1, M == N, no row/column scales); 2: fused top-k (topk != null)
+struct PeerArgs {
+  float* const* tables;
+  int n_peers, rank;
+};
+
 static int gemm_planes_impl(int32_t kind, const void* A, int64_t lda, const void* B, int64_t ldb,
                             int64_t plane_stride, int32_t planes, int64_t M, int64_t N, int64_t K, float* C, int64_t ldc,
                             const float* rs, const float* cs, double scale, int mode, const TopkArgs* topk,
-                            lgc_stream_t stream_) {
+                            lgc_stream_t stream_, const PeerArgs* peers = nullptr) {
   const int esize = kind == 0 ? 2 : 1;
   LGC_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "gemm: operands must be 16-byte aligned");
   LGC_REQUIRE((lda * esize) % 16 == 0 && (ldb * esize) % 16 == 0 && (plane_stride * esize) % 16 == 0,
@@ -763,9 +796,15 @@ static int gemm_planes_impl(int32_t kind, const void* A, int64_t lda, const void
   p.k_elems_per_kb = k_elems;
   p.chunk_kb = kind == 0 ? g_chunk_kb : p.num_kb;  // int32 accumulation is exact: one chunk
   p.mode = 0; p.segs = 1;
+  p.n_peers = 0; p.rank_slot = 0; p.n_ranks = 1;
+  if (peers) {
+    p.n_peers = peers->n_peers; p.rank_slot = peers->rank; p.n_ranks = peers->n_peers;
+    for (int r = 0; r < peers->n_peers; ++r) p.Cpeer[r] = peers->tables[r];
+  }
   cudaStream_t stream = (cudaStream_t)stream_;
 
-  const bool pair = (g_use_pair || mode == 2) && M > kBlockM;
+  const bool pair = (g_use_pair || mode == 2 || peers) && M > kBlockM;
+  if (peers && !pair) LGC_FAIL(LGC_ERR_UNSUPPORTED, "gemm bcast: needs more than 128 rows (CTA-pair kernel)");
   if (mode == 2 && !pair) LGC_FAIL(LGC_ERR_UNSUPPORTED, "resource_topk: needs more than 128 rows (CTA-pair kernel)");
   if (pair) {
     // CTA-pair kernel: 256-row tiles, each CTA stages half of the stacked plane rows of B
@@ -801,7 +840,8 @@ static int gemm_planes_impl(int32_t kind, const void* A, int64_t lda, const void
       p.excl = topk->excl; p.excl_stride = topk->excl_stride; p.excl_row0 = topk->excl_row0; p.k = topk->k;
     }
     int clusters = num_sms() / 2;
-    if (work < clusters) clusters = (int)work;
+    const int64_t my_work = ceil_div(work, (int64_t)p.n_ranks);
+    if (my_work < clusters) clusters = (int)(my_work > 0 ? my_work : 1);
     const int grid = 2 * clusters;
     bool launched = false;
 #define LGC_GEMM_PAIR_CASE(KD, PL, EP)                                                                          \
@@ -868,6 +908,19 @@ extern "C" int hs_gemm_planes_sym(const void* A, int64_t lda, const void* B, int
   if (rc) return rc;
   return gemm_planes_impl(1, A, lda, B, ldb, plane_stride, planes, N, N, K, C, ldc, nullptr, nullptr, scale, 1, nullptr,
                           stream_);
+}
+
+extern "C" int hs_gemm_planes_sym_bcast(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t plane_stride,
+                                        int32_t planes, int64_t N, int64_t K, float* const* peer_C_host, int32_t n_peers,
+                                        int32_t my_rank, int64_t ldc, double scale, lgc_stream_t stream_) {
+  LGC_REQUIRE(peer_C_host && n_peers >= 1 && n_peers <= 8 && my_rank >= 0 && my_rank < n_peers, "gemm bcast: 1..8 replicas");
+  for (int r = 0; r < n_peers; ++r)
+    LGC_REQUIRE(peer_C_host[r] && ((uintptr_t)peer_C_host[r] & 15) == 0, "gemm bcast: bad replica pointer");
+  int rc = check_gemm_args(1, A, lda, B, ldb, plane_stride, planes, N, N, K, peer_C_host[my_rank], ldc);
+  if (rc) return rc;
+  PeerArgs pa{peer_C_host, n_peers, my_rank};
+  return gemm_planes_impl(1, A, lda, B, ldb, plane_stride, planes, N, N, K, peer_C_host[my_rank], ldc, nullptr, nullptr, scale,
+                          1, nullptr, stream_, &pa);
 }
 
 extern "C" int64_t hs_resource_topk_scratch_bytes(int64_t M, int64_t N, int32_t planes) {

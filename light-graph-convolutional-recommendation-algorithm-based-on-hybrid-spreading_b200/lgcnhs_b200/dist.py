@@ -74,6 +74,32 @@ def _ipc_import(blob: bytes) -> int:
     return int(out.value)
 
 
+class PeerGroup:
+    """The ranks of one box as a peer-memory group: device buffers shared through CUDA IPC (every rank gets a pointer to
+    every rank's copy) and a stream-ordered device barrier over epoch flags in peer memory (lgc_peer_barrier_dev).
+    NCCL / gloo is used for the handle exchange only."""
+
+    def __init__(self, device: torch.device):
+        assert dist.is_initialized(), "PeerGroup needs an initialised process group"
+        self.rank, self.world, self.dev = dist.get_rank(), dist.get_world_size(), device
+        self.flags = torch.zeros(64, dtype=torch.int32, device=device)
+        self.epoch_dev = torch.zeros(1, dtype=torch.int32, device=device)
+        self.flag_ptrs = self.share(self.flags)
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    def share(self, t: torch.Tensor) -> list:
+        """Pointers to every rank's tensor of this call (same shape on all ranks), index = rank."""
+        blobs: list = [None] * self.world
+        dist.all_gather_object(blobs, _ipc_export(t))
+        return [t.data_ptr() if r == self.rank else _ipc_import(blobs[r]) for r in range(self.world)]
+
+    def barrier(self) -> None:
+        farr = (C.c_void_p * self.world)(*[C.c_void_p(p) for p in self.flag_ptrs])
+        check(lib().lgc_peer_barrier_dev(self.flags.data_ptr(), farr, self.rank, self.world, self.epoch_dev.data_ptr(),
+                                         torch.cuda.current_stream().cuda_stream), "peer barrier")
+
+
 class RowPartitionedPropagation:
     """K-layer propagation + layer mean with the rows of A_hat split over the ranks."""
 

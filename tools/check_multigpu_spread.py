@@ -37,6 +37,18 @@ parts = [torch.empty((ub[r + 1] - ub[r], 20), dtype=torch.int64, device=dev) for
 dist.all_gather(parts, idx.contiguous()) if len({p.shape for p in parts}) == 1 else [dist.broadcast(parts[r] if r != rank else idx.contiguous(), src=r) for r in range(world)]
 print(f"rank {rank}/{world}: G block [{jb[rank]},{jb[rank+1]}) and user block [{ub[rank]},{ub[rank+1]}) bit-identical={ok}; "
       f"sharded lambda-step {dt*1e3:.3f} ms -> {U/dt:.0f} users/s aggregate", flush=True)
+# fused GEMM + all-gather: the symmetric schedule dealt over the ranks, every rank ends with the full G, bit-identical
+from lgcnhs_b200.dist import PeerGroup  # noqa: E402
+group = PeerGroup(dev)
+Gall, peers = eng.general_w_allgather(group)
+torch.cuda.synchronize()
+same_all = torch.equal(Gall, G)
+Gall.fill_(float("nan"))
+eng.general_w_allgather(group, out=Gall, peer_ptrs=peers)
+torch.cuda.synchronize()
+same_all &= torch.equal(Gall, G)
+ok &= same_all
+print(f"rank {rank}/{world}: fused GEMM + all-gather G bit-identical to the single-GPU G: {same_all}", flush=True)
 flag = torch.tensor([1.0 if ok else 0.0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
