@@ -409,10 +409,11 @@ static int launch_spmm(const int32_t* rowptr, const int32_t* colidx, const float
     case 32: LGC_SPMM_LAUNCH(32, 4); break;
     case 64:
       {
-        // measured on B200 (tools/spmm_tune.py): with more than one full wave of CTAs, occupancy
-        // (32 regs, 64 warps/SM) beats per-warp ILP; with a single wave the deeper unroll wins
+        // measured on B200 (tools/spmm_tune.py, tools/partition_probe.py): with more than four full waves of CTAs,
+        // occupancy (32 regs, 64 warps/SM) beats per-warp ILP; below that the deeper unroll wins (per-rank launches of
+        // the 4- and 8-GPU partitions: 77 vs 88 us at 4 M non-zeros)
         int un = g_spmm_unroll;
-        if (un == 0) un = grid > (int64_t)num_sms() * 8 * 2 ? 2 : 4;
+        if (un == 0) un = grid > (int64_t)num_sms() * 8 * 4 ? 2 : 4;
         if (un == 8) LGC_SPMM_LAUNCH(64, 8);
         else if (un == 2) LGC_SPMM_LAUNCH(64, 2);
         else LGC_SPMM_LAUNCH(64, 4);

@@ -52,7 +52,7 @@ def partition_rows_by_nnz(rowptr: np.ndarray, parts: int, chunk_weight: float = 
     deg = np.diff(rowptr.astype(np.int64))
     if long_row is None:
         per_part = max(1.0, float(rowptr[-1] - rowptr[0]) / max(parts, 1))
-        long_row = int(min(2048, max(256, 2 ** int(round(np.log2(max(1.0, per_part * 1e-4)))))))
+        long_row = int(min(2048, max(256, 2 ** int(round(np.log2(max(1.0, per_part * 8e-5)))))))
     w = np.where(deg > long_row, chunk_weight, 1.0)
     cost = np.concatenate([[0.0], np.cumsum(deg * w + 1.0)])
     targets = cost[-1] * np.arange(1, parts, dtype=np.float64) / parts

@@ -19,6 +19,12 @@ LONG_ROW = 256
 CHUNK = 1024
 
 
+def long_row_for(nnz: int) -> int:
+    """Warp-per-row threshold of an SpMM launch over `nnz` non-zeros (power of two in [LONG_ROW, 2048])."""
+    t = 2 ** int(round(math.log2(max(1.0, nnz * 8e-5))))
+    return int(min(2048, max(LONG_ROW, t)))
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -138,10 +144,10 @@ class NormGraph:
             o = ((keys & 0xFFFFFFFF) + row_begin).to(torch.int32)
             self._orders[key] = o
             # warp-per-row threshold sized to the launch: a lone warp streams ~40 non-zeros per microsecond, so rows
-            # up to ~1e-4 x nnz(launch) hide inside the launch when issued first (tools/spmm_rows_probe.py, B200)
+            # up to ~8e-5 x nnz(launch) hide inside the launch when issued first (tools/spmm_rows_probe.py and
+            # tools/partition_probe.py, B200: 32 M nnz -> 2048, 16 M -> 1024, 4-8 M -> 512, <= 2.4 M -> 256)
             nnz = int(rp[-1] - rp[0])
-            t = 2 ** int(round(math.log2(max(1.0, nnz * 1e-4))))
-            self._long_rows[key] = int(min(2048, max(LONG_ROW, t)))
+            self._long_rows[key] = long_row_for(nnz)
         return o
 
     def long_row(self, row_begin: int = 0, row_end: Optional[int] = None) -> int:
@@ -246,13 +252,12 @@ class NormGraph:
             keys = ((mx - deg) << 32) | rows
             sort_u64(keys, bits=32 + max(1, mx.bit_length()))
             nnz = int(deg.sum())
-            t = 2 ** int(round(math.log2(max(1.0, nnz * 1e-4))))
             chunks = [self.chunk_range(a, b) for a, b in key][:2]
             while len(chunks) < 2:
                 chunks.append((0, 0))
             if len(key) > 2:
                 raise LgcnhsError("row_list: at most two row ranges per launch")
-            hit = ((keys & 0xFFFFFFFF).to(torch.int32), int(min(2048, max(LONG_ROW, t))), chunks)
+            hit = ((keys & 0xFFFFFFFF).to(torch.int32), long_row_for(nnz), chunks)
             self._lists[key] = hit
         return hit
 
