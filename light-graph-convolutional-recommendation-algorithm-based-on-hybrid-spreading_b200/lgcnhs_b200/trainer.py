@@ -193,23 +193,37 @@ class FusedBPRTrainer:
         return 2 * self.K * self.g.layer_bytes_compulsory(self.D) + batch * 12 * 4 * self.D + 7 * self.N * 4 * self.D
 
 
+def user_block(user_num: int, rank: int, world: int) -> tuple:
+    """Users [u0, u1) ranked by `rank` when the evaluation is sharded by user block."""
+    return user_num * rank // world, user_num * (rank + 1) // world
+
+
+def gather_user_blocks(idx_block: torch.Tensor, user_num: int, rank: int, world: int) -> torch.Tensor:
+    """All-gather of the per-rank (u1 - u0, k) id blocks into the full (user_num, k) list on every rank: the only
+    exchange of the sharded evaluation.  Blocks are padded to equal height for one all_gather_into_tensor; works on any
+    backend (NCCL on the GPUs, gloo in the CPU tests)."""
+    import torch.distributed as dist
+
+    k = int(idx_block.shape[1])
+    blk = (user_num + world - 1) // world
+    u0, u1 = user_block(user_num, rank, world)
+    pad = torch.full((blk, k), -1, dtype=idx_block.dtype, device=idx_block.device)
+    pad[: u1 - u0] = idx_block
+    out = torch.empty((world * blk, k), dtype=idx_block.dtype, device=idx_block.device)
+    dist.all_gather_into_tensor(out, pad)
+    rows = torch.cat([torch.arange(b - a, device=idx_block.device) + r * blk
+                      for r, (a, b) in enumerate(user_block(user_num, r, world) for r in range(world))])
+    return out[rows]
+
+
 def sharded_topk_layer0(model, user_num: int, item_num: int, seen: tuple, k: int, rank: int, world: int):
     """Full-rank evaluation sharded by USER BLOCK (SURVEY.md 8e "scoring + top-k: independent units"): rank r ranks users
     [U r / P, U (r+1) / P) with the fused score/top-k kernel; the only exchange is the gather of the (U, k) ids."""
-    import torch.distributed as dist
-
     xu = model.users_emb.weight.detach().contiguous()
     xi = model.items_emb.weight.detach().contiguous()
-    u0, u1 = user_num * rank // world, user_num * (rank + 1) // world
+    u0, u1 = user_block(user_num, rank, world)
     idx, _ = ops.score_topk(xu, xi, k, seen, fill=-float(1 << 10), u0=u0, u1=u1, want_values=False)
-    blk = (user_num + world - 1) // world
-    pad = torch.full((blk, k), -1, dtype=torch.int64, device=xu.device)
-    pad[: u1 - u0] = idx
-    out = torch.empty((world * blk, k), dtype=torch.int64, device=xu.device)
-    dist.all_gather_into_tensor(out, pad)
-    rows = torch.cat([torch.arange(user_num * r // world, user_num * (r + 1) // world, device=xu.device) - user_num * r // world
-                      + r * blk for r in range(world)])
-    return out[rows], idx
+    return gather_user_blocks(idx, user_num, rank, world), idx
 
 
 def choose_device() -> torch.device:

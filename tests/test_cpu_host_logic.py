@@ -116,6 +116,55 @@ def _gloo_worker(rank, world, port, q):
     q.put((rank, ok, [int(b) for b in bounds]))
 
 
+def _gloo_eval_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    sys.path[:0] = [PKG, ROOT]
+    import torch.distributed as dist
+
+    from lgcnhs_b200.dist import init_dist, partition_rows_by_nnz
+    from lgcnhs_b200.trainer import gather_user_blocks, user_block
+
+    init_dist("gloo")
+    ok = True
+    for U, k in ((7, 3), (100, 20), (101, 5)):
+        full = torch.arange(U * k, dtype=torch.int64).reshape(U, k) * 3 + 1      # what one GPU would return
+        u0, u1 = user_block(U, rank, world)
+        got = gather_user_blocks(full[u0:u1].clone(), U, rank, world)             # every rank contributes its block
+        ok &= torch.equal(got, full)
+    # users / items split of the distributed trainer: both halves partitioned by nnz, each rank owns one slice of each
+    rng = np.random.default_rng(1)
+    deg = np.r_[rng.integers(1, 50, 300), rng.zipf(1.6, 500).clip(max=400)]
+    rowptr = np.r_[0, np.cumsum(deg)]
+    split = 300
+    bu = partition_rows_by_nnz(rowptr[: split + 1], world)
+    bi = partition_rows_by_nnz(rowptr[split:] - rowptr[split], world) + split
+    ok &= bu[0] == 0 and bu[-1] == split and bi[0] == split and bi[-1] == 800
+    mine = int(rowptr[bu[rank + 1]] - rowptr[bu[rank]] + rowptr[bi[rank + 1]] - rowptr[bi[rank]])
+    tot = torch.tensor([mine])
+    dist.all_reduce(tot)
+    ok &= int(tot.item()) == int(rowptr[-1])                                       # the slices tile the graph
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, bool(ok)))
+
+
+def test_sharded_eval_gather_and_split_partition_gloo_world2():
+    """Host logic of the N-GPU evaluation (user blocks, padded all-gather, row reconstruction) and of the users/items
+    partition of the distributed trainer, on two gloo ranks."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + os.getpid() % 90
+    ps = [ctx.Process(target=_gloo_eval_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p_ in ps:
+        p_.start()
+    res = [q.get(timeout=180) for _ in ps]
+    for p_ in ps:
+        p_.join(timeout=60)
+    assert all(ok for _, ok in res)
+
+
 def test_row_partition_exchange_gloo_world2():
     import torch.multiprocessing as mp
 
