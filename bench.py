@@ -814,7 +814,14 @@ def main():
                                    f"train graph (U={d.n_users}, M={d.n_items}, nnz={nnz}, N={n})",
                        "l2": "inputs larger than L2 (CSR stream 8*nnz = %.0f MB per layer; X 42 MB is L2-resident by design)"
                              % (8 * nnz / 1e6),
-                       "parallelism": "1 GPU" if world == 1 else f"row partition by nnz over {world} GPUs, {args.mode} exchange"},
+                       "parallelism": "1 GPU" if world == 1 else
+                       f"row partition by nnz over {world} GPUs (users and items separately: {bool(args.split)}), one mixed launch per "
+                       f"layer and rank, {args.mode} exchange fused into the SpMM: "
+                       + ("every row stored ONCE to an NVSwitch multicast address (NVLS replicates it into all replicas)"
+                          if getattr(prop, "mcast", None) is not None else
+                          "every row stored into each peer's replica (CUDA IPC); multicast unavailable: "
+                          + str(getattr(prop, "mcast_error", "disabled"))[:160])
+                       + ", one device barrier per layer"},
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
         }

@@ -74,6 +74,121 @@ def _ipc_import(blob: bytes) -> int:
     return int(out.value)
 
 
+class _RawCuda:
+    """A (rows, cols) fp32 device buffer at a raw address, as a __cuda_array_interface__ object (torch.as_tensor maps it
+    zero-copy)."""
+
+    def __init__(self, ptr: int, shape: tuple):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2,
+                                         "strides": None}
+
+
+class MulticastBuffers:
+    """`n_bufs` buffers of `nbytes_each` bytes that exist on EVERY rank at the same offsets and are all bound to ONE
+    NVSwitch multicast object: a store to `mc_ptr(i) + off` by any rank is replicated by the switch into every rank's
+    copy (NVLS), so the per-layer all-gather of the partitioned SpMM leaves each GPU ONCE instead of once per peer
+    (8 x less NVLink egress at 8 GPUs).  Local reads go through the ordinary mapping `local_ptr(i)` of the rank's own
+    physical memory.
+
+    Driver API through cuda-python (cuMulticastCreate / AddDevice / BindMem, cuMemCreate / Map / SetAccess); the
+    multicast handle travels from rank 0 to the other ranks as a POSIX file descriptor over a Unix-domain socket.
+    Raises if the device / driver / fabric does not support multicast — callers fall back to per-peer stores."""
+
+    def __init__(self, nbytes_each: int, n_bufs: int, device: torch.device):
+        try:
+            from cuda.bindings import driver as cu
+        except ImportError:                                   # older cuda-python layout
+            from cuda import cuda as cu
+        import socket
+        import tempfile
+        import time
+
+        self.cu = cu
+        rank, world = dist.get_rank(), dist.get_world_size()
+        dev_index = device.index if device.index is not None else torch.cuda.current_device()
+
+        def ok(res, what):
+            err = res[0] if isinstance(res, tuple) else res
+            if int(err) != 0:
+                raise RuntimeError(f"multicast setup: {what} failed with {err}")
+            return res[1] if isinstance(res, tuple) and len(res) == 2 else (res[1:] if isinstance(res, tuple) else None)
+
+        torch.zeros(1, device=device)                         # make sure torch's primary context is current
+        cudev = ok(cu.cuDeviceGet(dev_index), "cuDeviceGet")
+        sup = ok(cu.cuDeviceGetAttribute(cu.CUdevice_attribute.CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, cudev), "attribute")
+        if not sup:
+            raise RuntimeError("multicast setup: CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED is 0")
+        fd_type = cu.CUmemAllocationHandleType.CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR
+        prop = cu.CUmulticastObjectProp()
+        prop.numDevices = world
+        prop.handleTypes = fd_type
+        prop.flags = 0
+        prop.size = int(nbytes_each) * n_bufs
+        gran = int(ok(cu.cuMulticastGetGranularity(prop, cu.CUmulticastGranularity_flags.CU_MULTICAST_GRANULARITY_RECOMMENDED),
+                      "cuMulticastGetGranularity"))
+        self.stride = (int(nbytes_each) + gran - 1) // gran * gran
+        size = self.stride * n_bufs
+        prop.size = size
+        # ---- the multicast object: created by rank 0, imported by the others through a passed file descriptor ----
+        name = [os.path.join(tempfile.gettempdir(), f"lgcnhs_mc_{os.getpid()}_{time.time_ns()}.sock")] if rank == 0 else [None]
+        dist.broadcast_object_list(name, src=0)
+        if rank == 0:
+            mc = ok(cu.cuMulticastCreate(prop), "cuMulticastCreate")
+            fd = int(ok(cu.cuMemExportToShareableHandle(mc, fd_type, 0), "cuMemExportToShareableHandle"))
+            srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+            srv.bind(name[0])
+            srv.listen(world)
+            dist.barrier()                                    # the socket exists
+            for _ in range(world - 1):
+                conn, _a = srv.accept()
+                socket.send_fds(conn, [b"mc"], [fd])
+                conn.close()
+            srv.close()
+            os.unlink(name[0])
+            os.close(fd)
+        else:
+            dist.barrier()
+            cli = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+            cli.connect(name[0])
+            _msg, fds, _f, _ad = socket.recv_fds(cli, 16, 1)
+            cli.close()
+            mc = ok(cu.cuMemImportFromShareableHandle(fds[0], fd_type), "cuMemImportFromShareableHandle")
+            os.close(fds[0])
+        ok(cu.cuMulticastAddDevice(mc, cudev), "cuMulticastAddDevice")
+        dist.barrier()                                        # every device has joined before memory is bound
+        # ---- this rank's physical memory, bound into the multicast object at offset 0 ----
+        aprop = cu.CUmemAllocationProp()
+        aprop.type = cu.CUmemAllocationType.CU_MEM_ALLOCATION_TYPE_PINNED
+        aprop.location.type = cu.CUmemLocationType.CU_MEM_LOCATION_TYPE_DEVICE
+        aprop.location.id = dev_index
+        aprop.requestedHandleTypes = fd_type
+        mem = ok(cu.cuMemCreate(size, aprop, 0), "cuMemCreate")
+        ok(cu.cuMulticastBindMem(mc, 0, mem, 0, size, 0), "cuMulticastBindMem")
+        dist.barrier()
+        acc = cu.CUmemAccessDesc()
+        acc.location.type = cu.CUmemLocationType.CU_MEM_LOCATION_TYPE_DEVICE
+        acc.location.id = dev_index
+        acc.flags = cu.CUmemAccess_flags.CU_MEM_ACCESS_FLAGS_PROT_READWRITE
+        self.mc_va = int(ok(cu.cuMemAddressReserve(size, gran, 0, 0), "cuMemAddressReserve (mc)"))
+        ok(cu.cuMemMap(self.mc_va, size, 0, mc, 0), "cuMemMap (mc)")
+        ok(cu.cuMemSetAccess(self.mc_va, size, [acc], 1), "cuMemSetAccess (mc)")
+        self.uc_va = int(ok(cu.cuMemAddressReserve(size, gran, 0, 0), "cuMemAddressReserve (local)"))
+        ok(cu.cuMemMap(self.uc_va, size, 0, mem, 0), "cuMemMap (local)")
+        ok(cu.cuMemSetAccess(self.uc_va, size, [acc], 1), "cuMemSetAccess (local)")
+        self.size, self.mc, self.mem, self.n_bufs, self.device = size, mc, mem, n_bufs, device
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    def mc_ptr(self, i: int) -> int:
+        return self.mc_va + i * self.stride
+
+    def local_ptr(self, i: int) -> int:
+        return self.uc_va + i * self.stride
+
+    def local_tensor(self, i: int, rows: int, cols: int) -> torch.Tensor:
+        return torch.as_tensor(_RawCuda(self.local_ptr(i), (rows, cols)), device=self.device)
+
+
 class PeerGroup:
     """The ranks of one box as a peer-memory group: device buffers shared through CUDA IPC (every rank gets a pointer to
     every rank's copy) and a stream-ordered device barrier over epoch flags in peer memory (lgc_peer_barrier_dev).
@@ -126,13 +241,32 @@ class RowPartitionedPropagation:
             self.parts = [[(bu[r], bu[r + 1]), (bi[r], bi[r + 1])] for r in range(self.world)]
         self.my_parts = [(a, b, self.g.chunk_range(a, b)) for a, b in self.parts[self.rank] if b > a]
         self.r0, self.r1 = self.parts[self.rank][0]
+        # exchange path: "p2p" first tries the NVSwitch multicast mapping (one store per row, replicated by the switch) and
+        # falls back to per-peer stores through CUDA IPC if any rank cannot set it up (LGCNHS_NO_MULTICAST=1 forces that)
+        self.mcast = None
+        if mode == "p2p" and self.world > 1 and os.environ.get("LGCNHS_NO_MULTICAST", "0") != "1":
+            try:
+                mc = MulticastBuffers(n_nodes * dim * 4, 4, self.dev)
+                good = 1
+            except Exception as e:        # noqa: BLE001  (any setup failure means: use the peer-store path)
+                mc, good = None, 0
+                self.mcast_error = repr(e)[:300]
+            flag = torch.tensor([good], device=self.dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 1:
+                self.mcast = mc
         # replicated activations: two ping-pong layers + TWO result buffers used alternately by successive calls.
         # The returned tensor aliases a buffer that peers write with remote stores; with a single result buffer a
         # faster rank's NEXT call could overwrite it while this rank's consumers still read it.  With two, the
         # buffer of call n is next written by call n+2, and a peer can only get there after passing a layer
         # barrier of call n+1, which this rank publishes stream-ordered AFTER its consumers of call n's result
         # (requirement: consume the result on the stream the propagation was issued on, or clone it).
-        self.bufs = [torch.zeros((n_nodes, dim), dtype=torch.float32, device=self.dev) for _ in range(4)]
+        if self.mcast is not None:
+            self.bufs = [self.mcast.local_tensor(i, n_nodes, dim) for i in range(4)]
+            for b in self.bufs:
+                b.zero_()
+        else:
+            self.bufs = [torch.zeros((n_nodes, dim), dtype=torch.float32, device=self.dev) for _ in range(4)]
         self._calls = 0
         self._flag = torch.zeros(1, dtype=torch.float32, device=self.dev)
         self.peer_ptrs: list[list[int]] = []
@@ -143,10 +277,13 @@ class RowPartitionedPropagation:
             self.flags = torch.zeros(64, dtype=torch.int32, device=self.dev)
             # barrier epoch, incremented by the barrier kernel itself: the sequence can be captured in a CUDA graph
             self.epoch_dev = torch.zeros(1, dtype=torch.int32, device=self.dev)
-            blobs = [_ipc_export(b) for b in self.bufs] + [_ipc_export(self.flags)]
+            blobs = ([None] * 4 if self.mcast is not None else [_ipc_export(b) for b in self.bufs]) + [_ipc_export(self.flags)]
             gathered: list = [None] * self.world
             dist.all_gather_object(gathered, blobs)
             for bi in range(4):
+                if self.mcast is not None:
+                    self.peer_ptrs.append([self.mcast.mc_ptr(bi)])     # ONE multicast address reaches every replica
+                    continue
                 ptrs = []
                 for r in range(self.world):
                     ptrs.append(self.bufs[bi].data_ptr() if r == self.rank else _ipc_import(gathered[r][bi]))

@@ -33,7 +33,7 @@ for mode, split in (("p2p", d.n_users), ("p2p", None), ("p2p-nccl", d.n_users), 
     torch.cuda.synchronize()
     same = bool((E - ref).abs().max() <= 2e-6 * ref.abs().max())   # per-launch summation paths: equal to round-off
     ok &= same
-    print(f"rank {rank}/{world} mode {mode}: parts {prop.parts[rank]} equal_to_single_gpu={same} "
+    print(f"rank {rank}/{world} mode {mode} (multicast={prop.mcast is not None}{'' if prop.mcast is not None or mode != 'p2p' else ' [' + getattr(prop, 'mcast_error', 'disabled') + ']'}): parts {prop.parts[rank]} equal_to_single_gpu={same} "
           f"max|diff|={(E - ref).abs().max().item():.3e}", flush=True)
     dist.barrier()
 flag = torch.tensor([1.0 if ok else 0.0], device=dev)

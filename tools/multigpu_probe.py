@@ -61,7 +61,7 @@ for split in (None, d.n_users):
     t_bar = timed(with_barrier)
     t_full = timed(lambda: prop.propagate_mean(x0, 3), reps=5) / 3
     nnz = sum(int(g.rowptr[b]) - int(g.rowptr[a]) for a, b, _ in prop.my_parts)
-    print(f"rank {rank}/{world} split={'users/items' if split else 'single'} parts={[(a, b) for a, b, _ in prop.my_parts]} "
+    print(f"rank {rank}/{world} multicast={prop.mcast is not None} split={'users/items' if split else 'single'} parts={[(a, b) for a, b, _ in prop.my_parts]} "
           f"nnz={nnz}: local {t_local:.1f} us ({nnz / t_local / 1e3:.1f} Gnnz/s) | +peer stores {t_store:.1f} us | ONE mixed launch "
           f"{t_mixed:.1f} us | "
           f"+barrier {t_bar:.1f} us | full layer {t_full:.1f} us", flush=True)
