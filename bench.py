@@ -518,8 +518,8 @@ def w_build_leg(d, dev, rank: int, world: int, steps: int = 3):
         from lgcnhs_b200.dist import PeerGroup
 
         group = PeerGroup(dev)
-        Gb, peers = eng.general_w_allgather(group, operands=operands)
-        run = lambda: eng.general_w_allgather(group, operands=operands, out=Gb, peer_ptrs=peers)  # noqa: E731
+        Gb, shared = eng.general_w_allgather(group, operands=operands)
+        run = lambda: eng.general_w_allgather(group, operands=operands, shared=shared)  # noqa: E731
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
@@ -549,11 +549,14 @@ def w_build_leg(d, dev, rank: int, world: int, steps: int = 3):
     tm, tn = (M + 255) // 256, (M + 63) // 64
     computed = sum(min(tm, ((n_ + 1) * 64 - 1) // 256 + 1) for n_ in range(tn)) / float(tm * tn)
     del operands, Gb, eng, run
+    shared = None
     torch.cuda.empty_cache()
     return {"workload": f"G = A^T K_u^-1 A on the ml-20m shape ({U}x{M}, nnz(A)={sel.size}), "
                         + ("symmetric tile schedule on 1 GPU" if world == 1 else
                            f"symmetric tile schedule dealt round-robin over {world} GPUs, tiles + mirrors stored into every "
-                           "replica over NVLink (fused GEMM + all-gather), two device barriers"),
+                           "replica over NVLink (fused GEMM + all-gather; " + ("one NVSwitch multicast store per element"
+                                                                              if len(shared[1]) == 1 else "one store per peer")
+                           + "), two device barriers"),
             "ms": round(ms, 3), "tflops": round(tf, 1), "scaling": "strong",
             "frac_of_bf16_peak": round(tf / (world * peak_sus), 4),
             "tiles_computed_frac": round(computed, 4), "tflops_issued": round(tf * computed, 1),

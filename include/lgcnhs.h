@@ -350,12 +350,13 @@ int hs_gemm_planes_sym(const void* A, int64_t lda, const void* B, int64_t ldb, i
                        int32_t planes, int64_t N, int64_t K, float* C, int64_t ldc, double scale,
                        lgc_stream_t stream);
 /* Multi-GPU form of hs_gemm_planes_sym: a fused GEMM + all-gather.  The cluster slots of the symmetric tile schedule
- * are dealt round-robin to the n_peers ranks; every computed tile (and its mirror) is stored into ALL replicas of C
- * (peer_C_host[r] = rank r's (N x ldc) buffer mapped through CUDA IPC, peer_C_host[my_rank] the local one), so each
- * rank ends with the full matrix after a barrier.  SURVEY 8e "W build: shard ... then all-gather W for scoring". */
+ * are dealt round-robin to the n_ranks ranks; every computed tile (and its mirror) is stored into the n_store targets
+ * store_C_host[0..n_store): either every rank's (N x ldc) replica mapped through CUDA IPC (n_store = n_ranks), or ONE
+ * NVSwitch multicast address bound to all replicas (n_store = 1) — each rank ends with the full matrix after a barrier.
+ * SURVEY 8e "W build: shard ... then all-gather W for scoring". */
 int hs_gemm_planes_sym_bcast(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t plane_stride,
-                             int32_t planes, int64_t N, int64_t K, float* const* peer_C_host, int32_t n_peers,
-                             int32_t my_rank, int64_t ldc, double scale, lgc_stream_t stream);
+                             int32_t planes, int64_t N, int64_t K, float* const* store_C_host, int32_t n_store,
+                             int32_t my_rank, int32_t n_ranks, int64_t ldc, double scale, lgc_stream_t stream);
 /* ------------------------------------------------------------------------------------
  * (S3+S4 fused) F = A . W and the per-user filtered top-k in ONE pass: the F tiles never
  * leave TMEM/registers.  Replaces np.dot(A, W) (model/SpreadMethod/model.py:98) followed by

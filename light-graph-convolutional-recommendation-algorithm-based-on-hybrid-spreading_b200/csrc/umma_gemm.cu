@@ -745,7 +745,8 @@ static size_t topk_scratch_bytes(int64_t M, int64_t N, int planes) {
 // mode 0: plain; 1: symmetric output (kind 1, M == N, no row/column scales); 2: fused top-k (topk != null)
 struct PeerArgs {
   float* const* tables;
-  int n_peers, rank;
+  int n_peers;   // replicas to store into (1 with an NVSwitch multicast address)
+  int rank, n_ranks;
 };
 
 static int gemm_planes_impl(int32_t kind, const void* A, int64_t lda, const void* B, int64_t ldb,
@@ -798,7 +799,7 @@ static int gemm_planes_impl(int32_t kind, const void* A, int64_t lda, const void
   p.mode = 0; p.segs = 1;
   p.n_peers = 0; p.rank_slot = 0; p.n_ranks = 1;
   if (peers) {
-    p.n_peers = peers->n_peers; p.rank_slot = peers->rank; p.n_ranks = peers->n_peers;
+    p.n_peers = peers->n_peers; p.rank_slot = peers->rank; p.n_ranks = peers->n_ranks;
     for (int r = 0; r < peers->n_peers; ++r) p.Cpeer[r] = peers->tables[r];
   }
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -911,16 +912,17 @@ extern "C" int hs_gemm_planes_sym(const void* A, int64_t lda, const void* B, int
 }
 
 extern "C" int hs_gemm_planes_sym_bcast(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t plane_stride,
-                                        int32_t planes, int64_t N, int64_t K, float* const* peer_C_host, int32_t n_peers,
-                                        int32_t my_rank, int64_t ldc, double scale, lgc_stream_t stream_) {
-  LGC_REQUIRE(peer_C_host && n_peers >= 1 && n_peers <= 8 && my_rank >= 0 && my_rank < n_peers, "gemm bcast: 1..8 replicas");
-  for (int r = 0; r < n_peers; ++r)
-    LGC_REQUIRE(peer_C_host[r] && ((uintptr_t)peer_C_host[r] & 15) == 0, "gemm bcast: bad replica pointer");
-  int rc = check_gemm_args(1, A, lda, B, ldb, plane_stride, planes, N, N, K, peer_C_host[my_rank], ldc);
+                                        int32_t planes, int64_t N, int64_t K, float* const* store_C_host, int32_t n_store,
+                                        int32_t my_rank, int32_t n_ranks, int64_t ldc, double scale, lgc_stream_t stream_) {
+  LGC_REQUIRE(store_C_host && n_store >= 1 && n_store <= 8, "gemm bcast: 1..8 store targets");
+  LGC_REQUIRE(n_ranks >= 1 && n_ranks <= 64 && my_rank >= 0 && my_rank < n_ranks, "gemm bcast: bad rank");
+  for (int r = 0; r < n_store; ++r)
+    LGC_REQUIRE(store_C_host[r] && ((uintptr_t)store_C_host[r] & 15) == 0, "gemm bcast: bad store target");
+  int rc = check_gemm_args(1, A, lda, B, ldb, plane_stride, planes, N, N, K, store_C_host[0], ldc);
   if (rc) return rc;
-  PeerArgs pa{peer_C_host, n_peers, my_rank};
-  return gemm_planes_impl(1, A, lda, B, ldb, plane_stride, planes, N, N, K, peer_C_host[my_rank], ldc, nullptr, nullptr, scale,
-                          1, nullptr, stream_, &pa);
+  PeerArgs pa{store_C_host, n_store, my_rank, n_ranks};
+  return gemm_planes_impl(1, A, lda, B, ldb, plane_stride, planes, N, N, K, store_C_host[0], ldc, nullptr, nullptr, scale, 1,
+                          nullptr, stream_, &pa);
 }
 
 extern "C" int64_t hs_resource_topk_scratch_bytes(int64_t M, int64_t N, int32_t planes) {

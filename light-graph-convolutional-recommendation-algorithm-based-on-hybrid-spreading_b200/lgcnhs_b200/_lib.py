@@ -72,7 +72,8 @@ _SIGS = {
     "hs_gemm_planes_simt": (C.c_int, [_i32, _p, _i64, _p, _i64, _i64, _i32, _i64, _i64, _i64, _p, _i64, _p, _p,
                                       _f64, _p]),
     "hs_gemm_planes_sym": (C.c_int, [_p, _i64, _p, _i64, _i64, _i32, _i64, _i64, _p, _i64, _f64, _p]),
-    "hs_gemm_planes_sym_bcast": (C.c_int, [_p, _i64, _p, _i64, _i64, _i32, _i64, _i64, C.POINTER(_p), _i32, _i32, _i64, _f64, _p]),
+    "hs_gemm_planes_sym_bcast": (C.c_int, [_p, _i64, _p, _i64, _i64, _i32, _i64, _i64, C.POINTER(_p), _i32, _i32, _i32, _i64, _f64,
+                                           _p]),
     "hs_resource_topk_scratch_bytes": (_i64, [_i64, _i64, _i32]),
     "hs_resource_topk": (C.c_int, [_p, _i64, _p, _i64, _i64, _i32, _i64, _i64, _i64, _p, _f64, _p, _i64, _i64, _i32, _p, _p,
                                    _p, _i64, _p]),

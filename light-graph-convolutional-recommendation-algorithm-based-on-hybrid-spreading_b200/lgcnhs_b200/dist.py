@@ -209,6 +209,24 @@ class PeerGroup:
         dist.all_gather_object(blobs, _ipc_export(t))
         return [t.data_ptr() if r == self.rank else _ipc_import(blobs[r]) for r in range(self.world)]
 
+    def shared_matrix(self, rows: int, ld: int):
+        """A (rows, ld) fp32 matrix that exists on every rank, with the store targets that reach ALL copies: one NVSwitch
+        multicast address when available, else every rank's copy through CUDA IPC.  Returns (local tensor, targets)."""
+        mc, good = None, 0
+        if os.environ.get("LGCNHS_NO_MULTICAST", "0") != "1":
+            try:
+                mc = MulticastBuffers(rows * ld * 4, 1, self.dev)
+                good = 1
+            except Exception as e:        # noqa: BLE001
+                self.mcast_error = repr(e)[:300]
+        flag = torch.tensor([good], device=self.dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 1:
+            self._keep = getattr(self, "_keep", []) + [mc]
+            return mc.local_tensor(0, rows, ld), [mc.mc_ptr(0)]
+        t = torch.empty((rows, ld), dtype=torch.float32, device=self.dev)
+        return t, self.share(t)
+
     def barrier(self) -> None:
         farr = (C.c_void_p * self.world)(*[C.c_void_p(p) for p in self.flag_ptrs])
         check(lib().lgc_peer_barrier_dev(self.flags.data_ptr(), farr, self.rank, self.world, self.epoch_dev.data_ptr(),

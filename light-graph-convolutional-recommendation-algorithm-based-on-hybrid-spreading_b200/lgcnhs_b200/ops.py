@@ -725,25 +725,27 @@ class SpreadingEngine:
             self.G = G
         return G
 
-    def general_w_allgather(self, group, operands=None, out: Optional[torch.Tensor] = None, peer_ptrs=None):
+    def general_w_allgather(self, group, operands=None, shared=None):
         """Multi-GPU G = A^T K_u^-1 A as a fused GEMM + all-gather (hs_gemm_planes_sym_bcast): the cluster slots of the
         symmetric tile schedule are dealt round-robin to the ranks of `group` (lgcnhs_b200.dist.PeerGroup) and every
-        computed tile and its mirror are stored into every rank's G over NVLink.  Returns (G, peer_ptrs); G is complete
-        on every rank after the group barrier this call ends with."""
+        computed tile and its mirror are stored into every rank's G over NVLink — through ONE NVSwitch multicast address
+        when the box supports it, else into each peer's replica through CUDA IPC.  `shared` = the value a previous call
+        returned (re-uses the shared G buffers).  Returns (G, shared); G is complete on every rank after the group
+        barrier this call ends with."""
         At, Q, shift = self.pack_g_operands() if operands is None else operands
         M = self.M
-        if out is None:
-            out = torch.empty((M, _pad(M, 4)), dtype=torch.float32, device=self.dev)[:, :M]
-        if peer_ptrs is None:
-            peer_ptrs = group.share(out)
-        arr = (C.c_void_p * group.world)(*[C.c_void_p(p) for p in peer_ptrs])
+        ldc = _pad(M, 4)
+        if shared is None:
+            shared = group.shared_matrix(M, ldc)
+        G, targets = shared
+        arr = (C.c_void_p * len(targets))(*[C.c_void_p(p) for p in targets])
         group.barrier()     # nobody still reads / writes the previous contents of any replica
         check(lib().hs_gemm_planes_sym_bcast(_ptr(At), int(At.stride(0)), _ptr(Q), int(Q.stride(1)), int(Q.stride(0)),
-                                             int(Q.shape[0]), M, self.U, arr, group.world, group.rank, int(out.stride(0)),
+                                             int(Q.shape[0]), M, self.U, arr, len(targets), group.rank, group.world, ldc,
                                              2.0 ** (-shift), _stream()), "gemm planes (symmetric, all-gather)")
         group.barrier()
-        self.G = out
-        return out, peer_ptrs
+        self.G = G[:, :M]
+        return self.G, shared
 
     def cooccurrence(self, operands=None) -> torch.Tensor:
         """C = A^T A (common-preference counts, metrics/diversity.py:104) — both operands 0/1, exact int32

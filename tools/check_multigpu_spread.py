@@ -40,15 +40,18 @@ print(f"rank {rank}/{world}: G block [{jb[rank]},{jb[rank+1]}) and user block [{
 # fused GEMM + all-gather: the symmetric schedule dealt over the ranks, every rank ends with the full G, bit-identical
 from lgcnhs_b200.dist import PeerGroup  # noqa: E402
 group = PeerGroup(dev)
-Gall, peers = eng.general_w_allgather(group)
+Gall, shared = eng.general_w_allgather(group)
 torch.cuda.synchronize()
 same_all = torch.equal(Gall, G)
-Gall.fill_(float("nan"))
-eng.general_w_allgather(group, out=Gall, peer_ptrs=peers)
+shared[0].fill_(float("nan"))
+torch.cuda.synchronize()
+dist.barrier()
+Gall, shared = eng.general_w_allgather(group, shared=shared)
 torch.cuda.synchronize()
 same_all &= torch.equal(Gall, G)
 ok &= same_all
-print(f"rank {rank}/{world}: fused GEMM + all-gather G bit-identical to the single-GPU G: {same_all}", flush=True)
+print(f"rank {rank}/{world}: fused GEMM + all-gather G ({'multicast' if len(shared[1]) == 1 else 'peer stores'}) bit-identical to "
+      f"the single-GPU G: {same_all}", flush=True)
 flag = torch.tensor([1.0 if ok else 0.0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
