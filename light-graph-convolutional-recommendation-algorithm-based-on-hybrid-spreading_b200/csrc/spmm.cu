@@ -19,8 +19,6 @@
 //   * the BCAST variant stores each finished row into every peer's replica (NVLink P2P
 //     stores): the per-layer all-gather of the row-partitioned multi-GPU path is fused into
 //     the SpMM epilogue.
-#include <cooperative_groups.h>
-
 #include "common.cuh"
 
 namespace lgc {
@@ -268,12 +266,13 @@ __global__ void peer_barrier_dev_kernel(const int32_t* __restrict__ local_flags,
 // ------------------------------------------------------------------------------------------------------------------
 // Small graphs: ALL K layers (+ the layer mean) in ONE cooperative launch.
 // At the ML-100K / Douban shapes a layer moves 0.4 us worth of compulsory bytes; as separate launches each layer costs
-// ~17 us (grid launch + drain + the serial (colidx, val) -> gather latency chain of the longest row).  Here the grid is
-// resident for the whole call (one CTA per SM slot, cudaLaunchCooperativeKernel), work is cut into warp-sized UNITS of
-// at most kCoopUnit non-zeros — a row, or a piece of a long row whose partial sums are combined in unit order after a
-// grid barrier (deterministic, no float atomics) — and layers are separated by grid barriers instead of launches.
+// ~15 us (grid launch + drain + the serial (colidx, val) -> gather latency chain of the longest row).  Here the grid is
+// resident for the whole call (cudaLaunchCooperativeKernel), work is cut by the host into warp-sized UNITS of at most 128
+// non-zeros — a row, or a piece of a long row whose partial sums are combined in unit order after a grid barrier
+// (deterministic, no float atomics) — and layers are separated by grid barriers instead of launches.
+// Measured (profiles/r2_coop_probe.txt): with cooperative_groups' grid.sync the call was 2-3x slower than three launches;
+// with the hand-written barrier below it is ~10 % faster at ML-100K and equal at the Douban shape, so it stays opt-in.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kCoopUnit = 128;
 
 struct CoopParams {
   const int32_t* rowptr;
