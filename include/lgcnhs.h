@@ -114,6 +114,11 @@ int lgc_seen_csr_workspace_bytes(int64_t n_pairs, size_t* bytes_host);
 int lgc_seen_csr(const int64_t* users, const int64_t* items, int64_t n_pairs, int64_t n_users,
                  int64_t n_items, int32_t* rowptr, int32_t* idx, int64_t* n_unique_host,
                  void* workspace, size_t workspace_bytes, lgc_stream_t stream);
+/* lgc_unique_u64: the distinct keys, ascending (torch.unique of the format converters utils/graph.py:12-50, which the
+ * reference obtains through a dense (U+M)^2 matrix); keys is clobbered, out needs room for n keys. */
+int lgc_unique_u64_workspace_bytes(int64_t n, size_t* bytes_host);
+int lgc_unique_u64(uint64_t* keys, uint64_t* out, int64_t n, int32_t bits, int64_t* n_unique_host,
+                   void* workspace, size_t workspace_bytes, lgc_stream_t stream);
 int lgc_sort_u64_workspace_bytes(int64_t n, size_t* bytes_host);
 int lgc_sort_u64(uint64_t* keys, uint64_t* tmp, int64_t n, int32_t bits, void* workspace,
                  size_t workspace_bytes, lgc_stream_t stream);

@@ -113,6 +113,16 @@ __global__ void head_flags_kernel(const uint64_t* __restrict__ keys, int64_t n, 
   flags[e] = (e == 0 || keys[e] != keys[e - 1]) ? 1u : 0u;
 }
 
+// sorted keys + exclusive scan of the head flags -> the distinct keys, ascending
+__global__ void compact_unique_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ pos, int64_t n,
+                                      uint64_t* __restrict__ out, int64_t* __restrict__ n_unique) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const bool head = e == 0 || keys[e] != keys[e - 1];
+  if (head) out[pos[e]] = keys[e];
+  if (e == n - 1) *n_unique = (int64_t)pos[e] + (head ? 1 : 0);
+}
+
 // sorted keys + exclusive scan of the head flags -> deduplicated CSR (rowptr over users, ascending item ids)
 __global__ void unique_csr_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ pos, int64_t n,
                                   int64_t n_users, int64_t n_items, int32_t* __restrict__ rowptr, int32_t* __restrict__ idx,
@@ -307,5 +317,54 @@ extern "C" int lgc_sort_u64(uint64_t* keys, uint64_t* tmp, int64_t n, int32_t bi
   if (!res) LGC_FAIL(LGC_ERR_CUDA, "sort: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   note_launch(launches);
   if (res != keys) LGC_CUDA(cudaMemcpyAsync(keys, res, sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToDevice, stream));
+  return LGC_OK;
+}
+
+// sorted, deduplicated copy of 64-bit keys (torch.unique of the format converters, utils/graph.py:12-50): keys is
+// clobbered, out receives the distinct keys ascending, *n_unique_host their number (one D2H sync)
+extern "C" int lgc_unique_u64_workspace_bytes(int64_t n, size_t* bytes_host) {
+  LGC_REQUIRE(bytes_host && n >= 0, "unique workspace: bad arguments");
+  const int64_t m = n > 0 ? n : 1;
+  size_t words = ingest::sort_table_words(m);
+  const size_t sw = ingest::scan_scratch_words(m);
+  if (sw > words) words = sw;
+  *bytes_host = align_up(sizeof(uint64_t) * (size_t)m, 256) + align_up(sizeof(uint32_t) * (size_t)m, 256) +
+                align_up(words * sizeof(uint32_t), 256) + 256;
+  return LGC_OK;
+}
+
+extern "C" int lgc_unique_u64(uint64_t* keys, uint64_t* out, int64_t n, int32_t bits, int64_t* n_unique_host, void* workspace,
+                              size_t workspace_bytes, lgc_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LGC_REQUIRE(n_unique_host && n >= 0 && bits >= 1 && bits <= 64, "unique: bad arguments");
+  if (n == 0) { *n_unique_host = 0; return LGC_OK; }
+  LGC_REQUIRE(keys && out && workspace, "unique: null pointer");
+  size_t need = 0;
+  lgc_unique_u64_workspace_bytes(n, &need);
+  if (workspace_bytes < need) LGC_FAIL(LGC_ERR_WORKSPACE, "unique: workspace %zu < %zu", workspace_bytes, need);
+  char* ws = (char*)workspace;
+  const size_t kb = align_up(sizeof(uint64_t) * (size_t)n, 256);
+  const size_t fb = align_up(sizeof(uint32_t) * (size_t)n, 256);
+  uint64_t* tmp = (uint64_t*)ws;
+  uint32_t* flags = (uint32_t*)(ws + kb);
+  uint32_t* table = (uint32_t*)(ws + kb + fb);
+  size_t words = ingest::sort_table_words(n);
+  const size_t sw = ingest::scan_scratch_words(n);
+  if (sw > words) words = sw;
+  int64_t* n_unique_dev = (int64_t*)(ws + kb + fb + align_up(words * sizeof(uint32_t), 256));
+  int launches = 0;
+  uint64_t* sorted = ingest::radix_sort_u64(keys, tmp, n, bits, table, stream, &launches);
+  if (!sorted) LGC_FAIL(LGC_ERR_CUDA, "unique: radix sort launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  note_launch(launches);
+  const int T = 256;
+  head_flags_kernel<<<(unsigned)ceil_div(n, T), T, 0, stream>>>(sorted, n, flags);
+  LGC_LAUNCH_CHECK("head_flags");
+  const int sl = ingest::exclusive_scan_u32(flags, flags, n, table, stream);
+  if (sl < 0) LGC_FAIL(LGC_ERR_CUDA, "unique: scan launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  note_launch(sl);
+  compact_unique_kernel<<<(unsigned)ceil_div(n, T), T, 0, stream>>>(sorted, flags, n, out, n_unique_dev);
+  LGC_LAUNCH_CHECK("compact_unique");
+  LGC_CUDA(cudaMemcpyAsync(n_unique_host, n_unique_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+  LGC_CUDA(cudaStreamSynchronize(stream));
   return LGC_OK;
 }

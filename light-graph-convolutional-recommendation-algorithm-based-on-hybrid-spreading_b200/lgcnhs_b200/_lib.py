@@ -28,6 +28,8 @@ _SIGS = {
     "lgc_csr_build": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, C.POINTER(_i32), _p, _sz, _p]),
     "lgc_seen_csr_workspace_bytes": (C.c_int, [_i64, C.POINTER(_sz)]),
     "lgc_seen_csr": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _p, C.POINTER(_i64), _p, _sz, _p]),
+    "lgc_unique_u64_workspace_bytes": (C.c_int, [_i64, C.POINTER(_sz)]),
+    "lgc_unique_u64": (C.c_int, [_p, _p, _i64, _i32, C.POINTER(_i64), _p, _sz, _p]),
     "lgc_sort_u64_workspace_bytes": (C.c_int, [_i64, C.POINTER(_sz)]),
     "lgc_sort_u64": (C.c_int, [_p, _p, _i64, _i32, _p, _sz, _p]),
     "lgc_spmm_layer": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i64, _i32, _i64, _i64, _p, _i32, _p, _p, _f32, _f32,

@@ -574,6 +574,22 @@ def seen_csr(users: torch.Tensor, items: torch.Tensor, n_users: int, n_items: in
     return rowptr, idx[: n_unique.value].clone() if n_unique.value < n else idx[:n]
 
 
+def unique_u64(keys: torch.Tensor, bits: int = 64) -> torch.Tensor:
+    """Distinct values of non-negative int64 keys, ascending (own radix sort + scan + compaction, lgc_unique_u64); the
+    input tensor is clobbered."""
+    keys = _req(keys, torch.int64, "keys")
+    n = int(keys.numel())
+    if n == 0:
+        return keys
+    out = torch.empty_like(keys)
+    nb = C.c_size_t(0)
+    check(lib().lgc_unique_u64_workspace_bytes(n, C.byref(nb)), "unique workspace")
+    ws = torch.empty(nb.value, dtype=torch.uint8, device=keys.device)
+    cnt = C.c_int64(0)
+    check(lib().lgc_unique_u64(_ptr(keys), _ptr(out), n, int(bits), C.byref(cnt), _ptr(ws), nb.value, _stream()), "unique")
+    return out[: cnt.value]
+
+
 def sort_u64(keys: torch.Tensor, bits: int = 64) -> torch.Tensor:
     """Stable ascending radix sort of non-negative int64 keys on the device (lgc_sort_u64), in place; returns keys."""
     keys = _req(keys, torch.int64, "keys")

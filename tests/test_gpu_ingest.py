@@ -66,3 +66,27 @@ def test_row_order_longest_first(dev):
         o = gph.row_order(a, b).cpu().to(torch.int64)
         ref = torch.argsort(deg[a:b].cpu(), descending=True, stable=True) + a
         assert torch.equal(o, ref)
+
+
+def test_unique_and_graph_converters_on_device(dev):
+    """lgc_unique_u64 vs torch.unique, and the drop-in utils/graph.py converters on CUDA tensors (own sort/compaction) vs
+    the same converters on CPU tensors (torch.unique) — which the CPU tests pin to the reference's outputs."""
+    import _stub_const
+    from lgcnhs_b200 import ops
+
+    g = torch.Generator().manual_seed(3)
+    keys = torch.randint(0, 5000, (200_000,), generator=g, dtype=torch.int64)
+    assert torch.equal(ops.unique_u64(keys.clone().to(dev), bits=13).cpu(), torch.unique(keys))
+    _stub_const.install()
+    from lgcnhs_b200.synth import synth_shape
+    from utils import graph
+
+    d = synth_shape("ml-100k")
+    ei = torch.from_numpy(np.stack([d.users, d.items]))
+    ei = torch.cat([ei, ei[:, :500]], dim=1)                 # duplicates, unsorted
+    adj_cpu = graph.convertEdgeIndexToAdjMatrix(d.n_users, d.n_items, ei)
+    adj_dev = graph.convertEdgeIndexToAdjMatrix(d.n_users, d.n_items, ei.to(dev))
+    assert adj_dev.is_cuda and torch.equal(adj_dev.cpu(), adj_cpu)
+    back_cpu = graph.convertAdjMatrixToEdgeIndex(d.n_users, d.n_items, adj_cpu)
+    back_dev = graph.convertAdjMatrixToEdgeIndex(d.n_users, d.n_items, adj_dev)
+    assert torch.equal(back_dev.cpu(), back_cpu)
