@@ -558,6 +558,7 @@ def w_build_leg(d, dev, rank: int, world: int, steps: int = 3):
     # share of the (256 x 64) output tiles the symmetric schedule actually computes
     tm, tn = (M + 255) // 256, (M + 63) // 64
     computed = sum(min(tm, ((n_ + 1) * 64 - 1) // 256 + 1) for n_ in range(tn)) / float(tm * tn)
+    mcast = world > 1 and len(shared[1]) == 1
     del operands, Gb, eng, run
     shared = None
     torch.cuda.empty_cache()
@@ -565,7 +566,7 @@ def w_build_leg(d, dev, rank: int, world: int, steps: int = 3):
                         + ("symmetric tile schedule on 1 GPU" if world == 1 else
                            f"symmetric tile schedule dealt round-robin over {world} GPUs, tiles + mirrors stored into every "
                            "replica over NVLink (fused GEMM + all-gather; " + ("one NVSwitch multicast store per element"
-                                                                              if len(shared[1]) == 1 else "one store per peer")
+                                                                              if mcast else "one store per peer")
                            + "), two device barriers"),
             "ms": round(ms, 3), "tflops": round(tf, 1), "scaling": "strong",
             "frac_of_bf16_peak": round(tf / (world * peak_sus), 4),

@@ -482,6 +482,18 @@ int64_t lgc_probe_gather_threads(void);
 int lgc_probe_gather(const float* table, int64_t n_rows, int32_t dim, int64_t n_gathers,
                      uint32_t seed, float* out, int64_t* gathers_done_host, lgc_stream_t stream);
 
+/* Measurement probe (tools/mcast_store_probe.py): the EXCHANGE half of the row-partitioned propagation with the gather
+ * removed — n_rows rows of 64 fp32 (row_list = device int32 row ids, or null for 0..n_rows-1) are copied from `src` to the
+ * same offsets of `dst`, which may be local, a CUDA-IPC peer mapping or an NVSwitch multicast address.  mode: 0 = 16 lanes x
+ * 16-byte stores per row (what lgc_spmm_rows_bcast issues), 1 = 32 lanes (two rows per instruction), 2 = one 256-byte
+ * cp.async.bulk (TMA) store per row from shared memory, 3 = one 8 KB cp.async.bulk store per 32 consecutive rows. */
+int lgc_probe_row_store(const float* src, float* dst, const int32_t* row_list, int64_t n_rows, int32_t mode,
+                        lgc_stream_t stream);
+/* The same copy by a PERSISTENT grid of n_ctas CTAs x 1024 threads walking the row list `passes` times; exclusive != 0
+ * launches it with enough dynamic shared memory that no other CTA shares its SMs (a dedicated-sender emulation). */
+int lgc_probe_row_store_persistent(const float* src, float* dst, const int32_t* row_list, int64_t n_rows,
+                                   int32_t n_ctas, int32_t passes, int32_t exclusive, lgc_stream_t stream);
+
 /* lgc_spmm_layer over an explicit LIST of rows (device int32[n_rows], any subset of the nodes; longest rows first gives
  * the best balance) plus up to two ranges of the long-row chunk list, in ONE launch; every finished row is stored into
  * n_peers replicas (n_peers = 1 with the local buffer: a plain local SpMM).  The multi-GPU partition gives a rank a slice

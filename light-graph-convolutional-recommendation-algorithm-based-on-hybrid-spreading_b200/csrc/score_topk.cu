@@ -2,9 +2,10 @@
 //   lgc_score_block : score = Xu . Xi^T with the seen-pair fill, standing in for
 //       torch.matmul + score[users, items] = -1024 at
 //       /root/reference/model/LightGCN/recommend.py:86,101,111 (== evaluation.py:34,49 and
-//       SpreadLightGCN/model.py:77,92,102).  fp32 FMA on CUDA cores: the contraction is only
-//       dim (64) long and the result must match an fp32 SGEMM to ~1e-7, so the tensor cores
-//       are not used here.
+//       SpreadLightGCN/model.py:77,92,102).  fp32 FMA on CUDA cores: this file is the bit-exact
+//       path (matches an fp32 SGEMM to ~1e-7; precise=True / LGCNHS_SCORE_FP32=1, k > 32, the
+//       fusion multiplier at other dims); the default full-rank eval runs on the tensor cores
+//       (score_topk_tc.cu, 3xTF32 split, 1e-5 tolerance).
 //   lgc_topk_rows   : torch.topk(score, k) (recommend.py:114) and the reference's real
 //       bottleneck, np.argsort(row)[::-1] + Python membership filter
 //       (/root/reference/model/SpreadMethod/recommend.py:35-47, 32.8 ms/user measured), as one

@@ -87,6 +87,8 @@ _SIGS = {
     "hs_hadamard": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _p]),
     "lgc_probe_gather_threads": (_i64, []),
     "lgc_probe_gather": (C.c_int, [_p, _i64, _i32, _i64, C.c_uint32, _p, C.POINTER(_i64), _p]),
+    "lgc_probe_row_store": (C.c_int, [_p, _p, _p, _i64, _i32, _p]),
+    "lgc_probe_row_store_persistent": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _i32, _p]),
     "lgc_ipc_get_handle": (C.c_int, [_p, _p]),
     "lgc_ipc_open_handle": (C.c_int, [_p, C.POINTER(_p)]),
     "lgc_ipc_close_handle": (C.c_int, [_p]),
