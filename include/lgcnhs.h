@@ -506,6 +506,44 @@ int lgc_spmm_rows_bcast(const int32_t* rowptr, const int32_t* colidx, const floa
                         const float* X0, float alpha, float beta, float* const* peer_Y_host,
                         int32_t n_peers, float* partial, int32_t* counters, lgc_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * Sparse-source layers.  autograd's backward of the propagation
+ * (/root/reference/model/LightGCN/train.py:140, loss.backward()) starts from dL/dE, which has at most 3 * batch non-zero rows
+ * (the users, positives and negatives of the mini-batch) out of U + M: the first gradient layer would gather nnz rows of
+ * which ~98 % are exact zeros.  src_mask / x0_row_mask = one bit per row of the source matrix, bit (r & 31) of word r >> 5,
+ * CLEAR = the row is all-zero; such rows are not gathered and groups of non-zeros without a live source are skipped.  The
+ * result is the one the unmasked call gives (the skipped terms are exact zeros).  dim 32 or 64.
+ *   lgc_row_mask_batch       : set (set != 0) the bits of rows users[b], n_users + pos[b], n_users + neg[b], or clear them
+ *                              again (set == 0; whole words — every set bit of the mask must come from the same batch).
+ *   lgc_spmm_layer_masked    : lgc_spmm_layer with the mask on X.
+ *   lgc_spmm_rows_bcast_masked: lgc_spmm_rows_bcast with the mask on X.
+ *   lgc_propagate_mean_masked: lgc_propagate_mean with the mask on X0, applied in the first layer (the only one whose
+ *                              source is X0 itself).
+ * ---------------------------------------------------------------------------------- */
+int lgc_row_mask_batch(uint32_t* mask, const int64_t* users, const int64_t* pos, const int64_t* neg, int64_t batch,
+                       int64_t n_users, int32_t set, lgc_stream_t stream);
+int lgc_spmm_layer_masked(const int32_t* rowptr, const int32_t* colidx, const float* val,
+                          const int32_t* chunk_row, const int32_t* chunk_start,
+                          const int32_t* row_chunk_base, int32_t chunk_begin, int32_t chunk_end,
+                          int64_t n_nodes, int32_t dim, int64_t row_begin, int64_t row_end,
+                          const int32_t* row_order, int32_t long_row, const float* X, const float* X0,
+                          float alpha, float beta, float* Y, float* partial, int32_t* counters,
+                          const uint32_t* src_mask, lgc_stream_t stream);
+int lgc_spmm_rows_bcast_masked(const int32_t* rowptr, const int32_t* colidx, const float* val,
+                               const int32_t* chunk_row, const int32_t* chunk_start,
+                               const int32_t* row_chunk_base, int32_t chunk_begin, int32_t chunk_end,
+                               int32_t chunk_begin2, int32_t chunk_end2, int64_t n_nodes, int32_t dim,
+                               const int32_t* row_list, int64_t n_rows, int32_t long_row, const float* X,
+                               const float* X0, float alpha, float beta, float* const* peer_Y_host,
+                               int32_t n_peers, float* partial, int32_t* counters, const uint32_t* src_mask,
+                               lgc_stream_t stream);
+int lgc_propagate_mean_masked(const int32_t* rowptr, const int32_t* colidx, const float* val,
+                              const int32_t* chunk_row, const int32_t* chunk_start,
+                              const int32_t* row_chunk_base, int32_t n_chunks, int64_t n_nodes,
+                              int32_t dim, int32_t n_layers, const int32_t* row_order, int32_t long_row,
+                              const float* X0, float* E, float* tmp0, float* tmp1, float* partial,
+                              int32_t* counters, const uint32_t* x0_row_mask, lgc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

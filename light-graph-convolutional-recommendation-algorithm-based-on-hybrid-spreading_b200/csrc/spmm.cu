@@ -43,11 +43,15 @@ __device__ __forceinline__ float4 ld_row4(const float* p) {
 // UN independent 128-bit gathers are in flight per lane, and the (colidx, val) metadata of the
 // next 32 non-zeros is requested before the gathers of the current 32 are issued, so the
 // dependent metadata -> gather chain is overlapped.
-template <int DIM, int UN>
+// MASK: `src_mask` has one bit per source row, clear = that row of X is all-zero.  Such rows are not gathered (their
+// terms are exact zeros, so the sum is unchanged) and groups of SUB*UN non-zeros without a live source are skipped
+// altogether: the first layer of the gradient propagation, whose input has <= 3 * batch non-zero rows, then costs the
+// (colidx, val) stream instead of one 4*DIM-byte gather per non-zero.
+template <int DIM, int UN, bool MASK = false>
 __device__ __forceinline__ float4 warp_gather_sum(const int32_t* __restrict__ colidx,
                                                   const float* __restrict__ val,
                                                   const float* __restrict__ X, int start, int end,
-                                                  int lane) {
+                                                  int lane, const uint32_t* __restrict__ src_mask = nullptr) {
   constexpr int LPR = DIM / 4;   // lanes per gathered row
   constexpr int SUB = 32 / LPR;  // rows in flight per warp-wide load
   const int sub = lane / LPR, li = lane % LPR;
@@ -66,7 +70,13 @@ __device__ __forceinline__ float4 warp_gather_sum(const int32_t* __restrict__ co
       v_next = __ldcs(val + base + 32 + lane);
     }
     const int n = min(32, end - base);
+    unsigned live = 0xffffffffu;
+    if (MASK) {
+      const bool on = base + lane < end && ((__ldg(src_mask + (c >> 5)) >> (c & 31)) & 1u);
+      live = __ballot_sync(0xffffffffu, on);
+    }
     for (int j = 0; j < n; j += SUB * UN) {
+      if (MASK && ((live >> j) & ((SUB * UN >= 32) ? 0xffffffffu : ((1u << (SUB * UN)) - 1u))) == 0u) continue;
       float4 x[UN];
       float w[UN];
 #pragma unroll
@@ -74,7 +84,7 @@ __device__ __forceinline__ float4 warp_gather_sum(const int32_t* __restrict__ co
         const int jj = j + u * SUB + sub;
         const int cc = __shfl_sync(0xffffffffu, c, jj & 31);
         const float vv = __shfl_sync(0xffffffffu, v, jj & 31);
-        const bool ok = jj < n;
+        const bool ok = jj < n && (!MASK || ((live >> (jj & 31)) & 1u));
         w[u] = ok ? vv : 0.f;
         x[u] = ok ? ld_row4(X + (size_t)cc * DIM + li * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
@@ -110,7 +120,7 @@ __device__ __forceinline__ void store_row4(float* Y, const PeerPtrs& peers, size
   }
 }
 
-template <int DIM, int NPEER, int UN>
+template <int DIM, int NPEER, int UN, bool MASK = false>
 __global__ void __launch_bounds__(kThreads)
 spmm_layer_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                   const float* __restrict__ val, const int32_t* __restrict__ chunk_row,
@@ -119,7 +129,7 @@ spmm_layer_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
                   const int32_t* __restrict__ row_order,
                   const float* __restrict__ X, const float* __restrict__ X0, float alpha, float beta,
                   float* __restrict__ Y, PeerPtrs peers, float* __restrict__ partial,
-                  int32_t* __restrict__ counters, int long_row) {
+                  int32_t* __restrict__ counters, int long_row, const uint32_t* __restrict__ src_mask) {
   constexpr int LPR = DIM / 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
@@ -132,7 +142,7 @@ spmm_layer_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
     const int row = row_order ? __ldg(row_order + (slot - row_begin)) : slot;
     const int start = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
     if (end - start > long_row) return;  // handled by the chunk CTAs
-    float4 acc = warp_gather_sum<DIM, UN>(colidx, val, X, start, end, lane);
+    float4 acc = warp_gather_sum<DIM, UN, MASK>(colidx, val, X, start, end, lane, src_mask);
     if (lane < LPR) {
       const size_t off = (size_t)row * DIM + lane * 4;
       if (beta != 0.f) {
@@ -161,7 +171,7 @@ spmm_layer_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
   const int cend = min(cstart + LGC_CHUNK, rend);
   constexpr int PER_WARP = LGC_CHUNK / kWarpsPerBlock;
   const int wstart = min(cstart + warp * PER_WARP, cend), wend = min(wstart + PER_WARP, cend);
-  float4 acc = warp_gather_sum<DIM, UN>(colidx, val, X, wstart, wend, lane);
+  float4 acc = warp_gather_sum<DIM, UN, MASK>(colidx, val, X, wstart, wend, lane, src_mask);
   if (lane < LPR) *reinterpret_cast<float4*>(&s_part[warp][lane * 4]) = acc;
   __syncthreads();
   const int nch = (rend - rstart + LGC_CHUNK - 1) / LGC_CHUNK;
@@ -384,17 +394,19 @@ static int launch_spmm(const int32_t* rowptr, const int32_t* colidx, const float
                        const int32_t* row_chunk_base, int chunk_begin, int chunk_end,
                        int64_t row_begin, int64_t row_end, const int32_t* row_order, int long_row_arg, int dim,
                        const float* X, const float* X0, float alpha, float beta, float* Y, const PeerPtrs& peers,
-                       float* partial, int32_t* counters, cudaStream_t stream, int chunk_begin2 = 0, int chunk_end2 = 0) {
+                       float* partial, int32_t* counters, cudaStream_t stream, int chunk_begin2 = 0, int chunk_end2 = 0,
+                       const uint32_t* src_mask = nullptr) {
   const int n_chunk_blocks1 = chunk_end - chunk_begin;
   const int n_chunk_blocks = n_chunk_blocks1 + (chunk_end2 - chunk_begin2);
   const int64_t n_rows = row_end - row_begin;
   const int64_t grid = n_chunk_blocks + ceil_div(n_rows, kWarpsPerBlock);
   if (grid == 0) return LGC_OK;
-#define LGC_SPMM_LAUNCH(D, UNR)                                                                   \
-  spmm_layer_kernel<D, NPEER, UNR><<<(unsigned)grid, kThreads, 0, stream>>>(                      \
+#define LGC_SPMM_LAUNCH_M(D, UNR, MASKED)                                                         \
+  spmm_layer_kernel<D, NPEER, UNR, MASKED><<<(unsigned)grid, kThreads, 0, stream>>>(              \
       rowptr, colidx, val, chunk_row, chunk_start, row_chunk_base, chunk_begin, n_chunk_blocks,   \
       chunk_begin2, n_chunk_blocks1, (int)row_begin, (int)row_end, row_order, X, X0, alpha, beta, Y, peers, partial, \
-      counters, long_row)
+      counters, long_row, src_mask)
+#define LGC_SPMM_LAUNCH(D, UNR) LGC_SPMM_LAUNCH_M(D, UNR, false)
   // Rows of LGC_LONG_ROW < nnz <= long_row take the warp-per-row path in this launch: it is cheaper than chunk
   // partials + ticket + re-read (ML-20M layer: 680 -> 525 us at long_row 1024), but a lone warp streams only ~40
   // non-zeros per microsecond, so only launches with enough work hide such rows, and they must be issued first
@@ -404,6 +416,16 @@ static int launch_spmm(const int32_t* rowptr, const int32_t* colidx, const float
   int long_row = g_spmm_long_row ? g_spmm_long_row : long_row_arg;
   if (long_row < LGC_LONG_ROW || !row_order) long_row = LGC_LONG_ROW;
   if (long_row > 2048) long_row = 2048;
+  if (src_mask) {
+    // sparse-source layer: few gathers survive the mask, so the deeper unroll costs nothing and one variant is enough
+    switch (dim) {
+      case 32: LGC_SPMM_LAUNCH_M(32, 4, true); break;
+      case 64: LGC_SPMM_LAUNCH_M(64, 4, true); break;
+      default: LGC_FAIL(LGC_ERR_UNSUPPORTED, "spmm (masked source): embedding dim %d not in {32,64}", dim);
+    }
+    LGC_LAUNCH_CHECK("spmm_layer_kernel (masked source)");
+    return LGC_OK;
+  }
   switch (dim) {
     case 32: LGC_SPMM_LAUNCH(32, 4); break;
     case 64:
@@ -422,6 +444,7 @@ static int launch_spmm(const int32_t* rowptr, const int32_t* colidx, const float
     default: LGC_FAIL(LGC_ERR_UNSUPPORTED, "spmm: embedding dim %d not in {32,64,128}", dim);
   }
 #undef LGC_SPMM_LAUNCH
+#undef LGC_SPMM_LAUNCH_M
   LGC_LAUNCH_CHECK("spmm_layer_kernel");
   return LGC_OK;
 }
@@ -465,13 +488,14 @@ extern "C" int lgc_spmm_long_row(int32_t long_row) {
   return LGC_OK;
 }
 
-extern "C" int lgc_spmm_layer(const int32_t* rowptr, const int32_t* colidx, const float* val,
-                              const int32_t* chunk_row, const int32_t* chunk_start,
-                              const int32_t* row_chunk_base, int32_t chunk_begin, int32_t chunk_end,
-                              int64_t n_nodes, int32_t dim, int64_t row_begin, int64_t row_end,
-                              const int32_t* row_order, int32_t long_row, const float* X, const float* X0,
-                              float alpha, float beta, float* Y, float* partial, int32_t* counters,
-                              lgc_stream_t stream) {
+// src_mask (optional): one bit per row of X, clear = the row is all-zero and is not gathered (lgc_spmm_layer_masked)
+static int spmm_layer_impl(const int32_t* rowptr, const int32_t* colidx, const float* val,
+                           const int32_t* chunk_row, const int32_t* chunk_start,
+                           const int32_t* row_chunk_base, int32_t chunk_begin, int32_t chunk_end,
+                           int64_t n_nodes, int32_t dim, int64_t row_begin, int64_t row_end,
+                           const int32_t* row_order, int32_t long_row, const float* X, const float* X0,
+                           float alpha, float beta, float* Y, float* partial, int32_t* counters,
+                           const uint32_t* src_mask, lgc_stream_t stream) {
   int rc = check_spmm_args(rowptr, colidx, val, chunk_row, chunk_start, row_chunk_base, chunk_begin,
                            chunk_end, n_nodes, row_begin, row_end, X, X0, beta, partial, counters);
   if (rc) return rc;
@@ -479,7 +503,30 @@ extern "C" int lgc_spmm_layer(const int32_t* rowptr, const int32_t* colidx, cons
   PeerPtrs none{};
   return launch_spmm<0>(rowptr, colidx, val, chunk_row, chunk_start, row_chunk_base, chunk_begin,
                         chunk_end, row_begin, row_end, row_order, long_row, dim, X, X0, alpha, beta, Y, none,
-                        partial, counters, (cudaStream_t)stream);
+                        partial, counters, (cudaStream_t)stream, 0, 0, src_mask);
+}
+
+extern "C" int lgc_spmm_layer(const int32_t* rowptr, const int32_t* colidx, const float* val,
+                              const int32_t* chunk_row, const int32_t* chunk_start,
+                              const int32_t* row_chunk_base, int32_t chunk_begin, int32_t chunk_end,
+                              int64_t n_nodes, int32_t dim, int64_t row_begin, int64_t row_end,
+                              const int32_t* row_order, int32_t long_row, const float* X, const float* X0,
+                              float alpha, float beta, float* Y, float* partial, int32_t* counters,
+                              lgc_stream_t stream) {
+  return spmm_layer_impl(rowptr, colidx, val, chunk_row, chunk_start, row_chunk_base, chunk_begin, chunk_end, n_nodes, dim,
+                         row_begin, row_end, row_order, long_row, X, X0, alpha, beta, Y, partial, counters, nullptr, stream);
+}
+
+extern "C" int lgc_spmm_layer_masked(const int32_t* rowptr, const int32_t* colidx, const float* val,
+                                     const int32_t* chunk_row, const int32_t* chunk_start,
+                                     const int32_t* row_chunk_base, int32_t chunk_begin, int32_t chunk_end,
+                                     int64_t n_nodes, int32_t dim, int64_t row_begin, int64_t row_end,
+                                     const int32_t* row_order, int32_t long_row, const float* X, const float* X0,
+                                     float alpha, float beta, float* Y, float* partial, int32_t* counters,
+                                     const uint32_t* src_mask, lgc_stream_t stream) {
+  LGC_REQUIRE(src_mask, "spmm masked: null source-row mask");
+  return spmm_layer_impl(rowptr, colidx, val, chunk_row, chunk_start, row_chunk_base, chunk_begin, chunk_end, n_nodes, dim,
+                         row_begin, row_end, row_order, long_row, X, X0, alpha, beta, Y, partial, counters, src_mask, stream);
 }
 
 extern "C" int lgc_spmm_layer_bcast(const int32_t* rowptr, const int32_t* colidx, const float* val,
@@ -518,12 +565,13 @@ extern "C" int lgc_spmm_layer_bcast(const int32_t* rowptr, const int32_t* colidx
 // buffer = plain local SpMM).  Used by the multi-GPU partition, where a rank owns a slice of the user rows AND a slice of
 // the item rows: one mixed launch keeps the short user rows and the chunked hub rows of the items in flight together,
 // which two back-to-back launches do not (measured: 61 / 44 Gnnz/s apart, 63 mixed).
-extern "C" int lgc_spmm_rows_bcast(const int32_t* rowptr, const int32_t* colidx, const float* val,
-                                   const int32_t* chunk_row, const int32_t* chunk_start, const int32_t* row_chunk_base,
-                                   int32_t chunk_begin, int32_t chunk_end, int32_t chunk_begin2, int32_t chunk_end2,
-                                   int64_t n_nodes, int32_t dim, const int32_t* row_list, int64_t n_rows, int32_t long_row,
-                                   const float* X, const float* X0, float alpha, float beta, float* const* peer_Y_host,
-                                   int32_t n_peers, float* partial, int32_t* counters, lgc_stream_t stream) {
+static int spmm_rows_bcast_impl(const int32_t* rowptr, const int32_t* colidx, const float* val,
+                                const int32_t* chunk_row, const int32_t* chunk_start, const int32_t* row_chunk_base,
+                                int32_t chunk_begin, int32_t chunk_end, int32_t chunk_begin2, int32_t chunk_end2,
+                                int64_t n_nodes, int32_t dim, const int32_t* row_list, int64_t n_rows, int32_t long_row,
+                                const float* X, const float* X0, float alpha, float beta, float* const* peer_Y_host,
+                                int32_t n_peers, float* partial, int32_t* counters, const uint32_t* src_mask,
+                                lgc_stream_t stream) {
   int rc = check_spmm_args(rowptr, colidx, val, chunk_row, chunk_start, row_chunk_base, chunk_begin, chunk_end, n_nodes, 0,
                            n_rows, X, X0, beta, partial, counters);
   if (rc) return rc;
@@ -542,13 +590,38 @@ extern "C" int lgc_spmm_rows_bcast(const int32_t* rowptr, const int32_t* colidx,
   case NP:                                                                                                        \
     return launch_spmm<NP>(rowptr, colidx, val, chunk_row, chunk_start, row_chunk_base, chunk_begin, chunk_end, 0, \
                            n_rows, row_list, long_row, dim, X, X0, alpha, beta, nullptr, peers, partial, counters, s, \
-                           chunk_begin2, chunk_end2)
+                           chunk_begin2, chunk_end2, src_mask)
   switch (n_peers) {
     LGC_ROWS(1); LGC_ROWS(2); LGC_ROWS(3); LGC_ROWS(4);
     LGC_ROWS(5); LGC_ROWS(6); LGC_ROWS(7); LGC_ROWS(8);
   }
 #undef LGC_ROWS
   return LGC_ERR_INVALID;
+}
+
+extern "C" int lgc_spmm_rows_bcast(const int32_t* rowptr, const int32_t* colidx, const float* val,
+                                   const int32_t* chunk_row, const int32_t* chunk_start, const int32_t* row_chunk_base,
+                                   int32_t chunk_begin, int32_t chunk_end, int32_t chunk_begin2, int32_t chunk_end2,
+                                   int64_t n_nodes, int32_t dim, const int32_t* row_list, int64_t n_rows, int32_t long_row,
+                                   const float* X, const float* X0, float alpha, float beta, float* const* peer_Y_host,
+                                   int32_t n_peers, float* partial, int32_t* counters, lgc_stream_t stream) {
+  return spmm_rows_bcast_impl(rowptr, colidx, val, chunk_row, chunk_start, row_chunk_base, chunk_begin, chunk_end, chunk_begin2,
+                              chunk_end2, n_nodes, dim, row_list, n_rows, long_row, X, X0, alpha, beta, peer_Y_host, n_peers,
+                              partial, counters, nullptr, stream);
+}
+
+extern "C" int lgc_spmm_rows_bcast_masked(const int32_t* rowptr, const int32_t* colidx, const float* val,
+                                          const int32_t* chunk_row, const int32_t* chunk_start,
+                                          const int32_t* row_chunk_base, int32_t chunk_begin, int32_t chunk_end,
+                                          int32_t chunk_begin2, int32_t chunk_end2, int64_t n_nodes, int32_t dim,
+                                          const int32_t* row_list, int64_t n_rows, int32_t long_row, const float* X,
+                                          const float* X0, float alpha, float beta, float* const* peer_Y_host,
+                                          int32_t n_peers, float* partial, int32_t* counters, const uint32_t* src_mask,
+                                          lgc_stream_t stream) {
+  LGC_REQUIRE(src_mask, "spmm rows masked: null source-row mask");
+  return spmm_rows_bcast_impl(rowptr, colidx, val, chunk_row, chunk_start, row_chunk_base, chunk_begin, chunk_end, chunk_begin2,
+                              chunk_end2, n_nodes, dim, row_list, n_rows, long_row, X, X0, alpha, beta, peer_Y_host, n_peers,
+                              partial, counters, src_mask, stream);
 }
 
 extern "C" int lgc_peer_barrier(const int32_t* local_flags, int32_t* const* peer_flags_host, int32_t my_rank,
@@ -580,12 +653,12 @@ extern "C" int lgc_peer_barrier_dev(const int32_t* local_flags, int32_t* const* 
   return LGC_OK;
 }
 
-extern "C" int lgc_propagate_mean(const int32_t* rowptr, const int32_t* colidx, const float* val,
-                                  const int32_t* chunk_row, const int32_t* chunk_start,
-                                  const int32_t* row_chunk_base, int32_t n_chunks, int64_t n_nodes,
-                                  int32_t dim, int32_t n_layers, const int32_t* row_order, int32_t long_row,
-                                  const float* X0, float* E, float* tmp0, float* tmp1, float* partial,
-                                  int32_t* counters, lgc_stream_t stream) {
+static int propagate_mean_impl(const int32_t* rowptr, const int32_t* colidx, const float* val,
+                               const int32_t* chunk_row, const int32_t* chunk_start,
+                               const int32_t* row_chunk_base, int32_t n_chunks, int64_t n_nodes,
+                               int32_t dim, int32_t n_layers, const int32_t* row_order, int32_t long_row,
+                               const float* X0, float* E, float* tmp0, float* tmp1, float* partial,
+                               int32_t* counters, const uint32_t* x0_row_mask, lgc_stream_t stream) {
   LGC_REQUIRE(X0 && E && n_layers >= 0, "propagate_mean: bad arguments");
   if (n_layers == 0) {
     LGC_CUDA(cudaMemcpyAsync(E, X0, sizeof(float) * (size_t)n_nodes * dim, cudaMemcpyDeviceToDevice,
@@ -600,13 +673,35 @@ extern "C" int lgc_propagate_mean(const int32_t* rowptr, const int32_t* colidx, 
     const bool last = (l == n_layers - 1);
     float* out = last ? E : bufs[l & 1];
     const float alpha = last ? 1.0f / (float)(n_layers + 1) : 1.0f;
-    int rc = lgc_spmm_layer(rowptr, colidx, val, chunk_row, chunk_start, row_chunk_base, 0, n_chunks,
-                            n_nodes, dim, 0, n_nodes, row_order, long_row, cur, X0, alpha, 1.0f, out, partial,
-                            counters, stream);
+    // only the first layer reads X0 as its source: that is where a sparse X0 (the BPR gradient) pays
+    int rc = spmm_layer_impl(rowptr, colidx, val, chunk_row, chunk_start, row_chunk_base, 0, n_chunks,
+                             n_nodes, dim, 0, n_nodes, row_order, long_row, cur, X0, alpha, 1.0f, out, partial,
+                             counters, l == 0 ? x0_row_mask : nullptr, stream);
     if (rc) return rc;
     cur = out;
   }
   return LGC_OK;
+}
+
+extern "C" int lgc_propagate_mean(const int32_t* rowptr, const int32_t* colidx, const float* val,
+                                  const int32_t* chunk_row, const int32_t* chunk_start,
+                                  const int32_t* row_chunk_base, int32_t n_chunks, int64_t n_nodes,
+                                  int32_t dim, int32_t n_layers, const int32_t* row_order, int32_t long_row,
+                                  const float* X0, float* E, float* tmp0, float* tmp1, float* partial,
+                                  int32_t* counters, lgc_stream_t stream) {
+  return propagate_mean_impl(rowptr, colidx, val, chunk_row, chunk_start, row_chunk_base, n_chunks, n_nodes, dim, n_layers,
+                             row_order, long_row, X0, E, tmp0, tmp1, partial, counters, nullptr, stream);
+}
+
+extern "C" int lgc_propagate_mean_masked(const int32_t* rowptr, const int32_t* colidx, const float* val,
+                                         const int32_t* chunk_row, const int32_t* chunk_start,
+                                         const int32_t* row_chunk_base, int32_t n_chunks, int64_t n_nodes,
+                                         int32_t dim, int32_t n_layers, const int32_t* row_order, int32_t long_row,
+                                         const float* X0, float* E, float* tmp0, float* tmp1, float* partial,
+                                         int32_t* counters, const uint32_t* x0_row_mask, lgc_stream_t stream) {
+  LGC_REQUIRE(x0_row_mask, "propagate_mean masked: null row mask");
+  return propagate_mean_impl(rowptr, colidx, val, chunk_row, chunk_start, row_chunk_base, n_chunks, n_nodes, dim, n_layers,
+                             row_order, long_row, X0, E, tmp0, tmp1, partial, counters, x0_row_mask, stream);
 }
 
 // All K layers + layer mean in one cooperative launch (small graphs).  The unit lists are built once per graph by the

@@ -355,6 +355,21 @@ __global__ void zero_rows_kernel(float* __restrict__ a, float* __restrict__ b, i
   if (b) *reinterpret_cast<float4*>(b + row * dim + li * 4) = z;
 }
 
+// one bit per node: set (or clear again) the bits of the rows a mini-batch touches — the non-zero rows of dL/dE, which the
+// first gradient-propagation layer uses to skip the gathers of all-zero rows (lgc_propagate_mean_masked).  Clearing stores
+// whole words: every set bit of the mask comes from the same batch.
+__global__ void row_mask_batch_kernel(uint32_t* __restrict__ mask, const int64_t* __restrict__ users,
+                                      const int64_t* __restrict__ pos, const int64_t* __restrict__ neg, int64_t batch,
+                                      int64_t n_users, int set) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= 3 * batch) return;
+  const int64_t bi = t / 3;
+  const int which = (int)(t % 3);
+  const int64_t row = which == 0 ? users[bi] : n_users + (which == 1 ? pos[bi] : neg[bi]);
+  if (set) atomicOr(mask + (row >> 5), 1u << (row & 31));
+  else mask[row >> 5] = 0u;
+}
+
 // ++step; hyper = {lr / (1 - beta1^step), sqrt(1 - beta2^step)}  — torch.optim.Adam's bias corrections
 // (float64 like the Python side of torch's single-tensor path, rounded once to fp32)
 __global__ void adam_hyper_kernel(long long* __restrict__ step, const float* __restrict__ lr, double beta1, double beta2,
@@ -491,6 +506,15 @@ extern "C" int lgc_zero_rows(float* a, float* b, int32_t dim, const int64_t* use
   const int64_t threads = 3 * batch * (dim / 4);
   zero_rows_kernel<<<(unsigned)ceil_div(threads, 256), 256, 0, (cudaStream_t)stream>>>(a, b, dim, users, pos, neg, batch, n_users);
   LGC_LAUNCH_CHECK("zero_rows_kernel");
+  return LGC_OK;
+}
+
+extern "C" int lgc_row_mask_batch(uint32_t* mask, const int64_t* users, const int64_t* pos, const int64_t* neg, int64_t batch,
+                                  int64_t n_users, int32_t set, lgc_stream_t stream) {
+  LGC_REQUIRE(mask && users && pos && neg && batch > 0 && n_users > 0, "row_mask_batch: null pointer / empty batch");
+  row_mask_batch_kernel<<<(unsigned)ceil_div(3 * batch, 256), 256, 0, (cudaStream_t)stream>>>(mask, users, pos, neg, batch,
+                                                                                             n_users, set);
+  LGC_LAUNCH_CHECK("row_mask_batch_kernel");
   return LGC_OK;
 }
 

@@ -38,6 +38,13 @@ _SIGS = {
                                        _f32, C.POINTER(_p), _i32, _p, _p, _p]),
     "lgc_spmm_rows_bcast": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i64, _i32, _p, _i64, _i32, _p, _p, _f32, _f32,
                                       C.POINTER(_p), _i32, _p, _p, _p]),
+    "lgc_spmm_layer_masked": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i64, _i32, _i64, _i64, _p, _i32, _p, _p, _f32, _f32,
+                                        _p, _p, _p, _p, _p]),
+    "lgc_spmm_rows_bcast_masked": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i64, _i32, _p, _i64, _i32, _p, _p,
+                                             _f32, _f32, C.POINTER(_p), _i32, _p, _p, _p, _p]),
+    "lgc_propagate_mean_masked": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i64, _i32, _i32, _p, _i32, _p, _p, _p, _p, _p, _p, _p,
+                                            _p]),
+    "lgc_row_mask_batch": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _i32, _p]),
     "lgc_peer_barrier": (C.c_int, [_p, C.POINTER(_p), _i32, _i32, _i32, _p]),
     "lgc_peer_barrier_dev": (C.c_int, [_p, C.POINTER(_p), _i32, _i32, _p, _p]),
     "lgc_adam_step_fused": (C.c_int, [_p, C.POINTER(_p), _i32, _p, _p, _p, _p, _i64, _i64, _f32, _f32, _f32, _p, _p]),

@@ -322,9 +322,12 @@ class RowPartitionedPropagation:
         # stream-ordered: completes only after every rank's SpMM (and its peer stores) has finished
         dist.all_reduce(self._flag)
 
-    def propagate_mean(self, x0: torch.Tensor, layers: int, result: Optional[int] = None) -> torch.Tensor:
+    def propagate_mean(self, x0: torch.Tensor, layers: int, result: Optional[int] = None,
+                       x0_row_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         """x0 is replicated on every rank; returns the replicated E = mean_l A_hat^l x0.
-        result: which of the two result buffers (0 / 1) receives it; default alternates between calls."""
+        result: which of the two result buffers (0 / 1) receives it; default alternates between calls.
+        x0_row_mask: x0 is zero outside the rows whose bit is set (ops.row_mask_words): the first layer skips the gathers
+        of the zero rows (p2p mode)."""
         g = self.g
         cur = x0
         res = 2 + ((self._calls & 1) if result is None else int(result))
@@ -335,7 +338,8 @@ class RowPartitionedPropagation:
             alpha = 1.0 / (layers + 1) if last else 1.0
             if self.mode == "p2p":
                 # ONE mixed launch over this rank's user rows and item rows (longest first across both)
-                g.spmm_rows_bcast(cur, x0, alpha, 1.0, self.peer_ptrs[oi], [(a, b) for a, b, _ in self.my_parts])
+                g.spmm_rows_bcast(cur, x0, alpha, 1.0, self.peer_ptrs[oi], [(a, b) for a, b, _ in self.my_parts],
+                                  src_mask=x0_row_mask if l == 0 else None)
                 self.peer_barrier()
             elif self.mode == "p2p-nccl":
                 for a, b, ch in self.my_parts:

@@ -170,8 +170,10 @@ class NormGraph:
 
     def spmm(self, X: torch.Tensor, X0: Optional[torch.Tensor] = None, alpha: float = 1.0, beta: float = 0.0,
              out: Optional[torch.Tensor] = None, row_begin: int = 0, row_end: Optional[int] = None,
-             chunks: Optional[tuple[int, int]] = None) -> torch.Tensor:
-        """out[r] = alpha * (sum_e val[e] X[colidx[e]] + beta X0[r]) for r in [row_begin, row_end)."""
+             chunks: Optional[tuple[int, int]] = None, src_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """out[r] = alpha * (sum_e val[e] X[colidx[e]] + beta X0[r]) for r in [row_begin, row_end).
+        src_mask (int32 words, one bit per row of X, see row_mask_words): rows whose bit is clear are all-zero and are not
+        gathered — same result, the cost of the (colidx, val) stream only."""
         X = _req(X, torch.float32, "X")
         n, dim = self.n_nodes, int(X.shape[1])
         if X.shape[0] != n:
@@ -184,11 +186,14 @@ class NormGraph:
         row_end = n if row_end is None else row_end
         cb, ce = chunks if chunks is not None else self.chunk_range(row_begin, row_end)
         partial, counters = self._scr(dim)
-        check(lib().lgc_spmm_layer(_ptr(self.rowptr), _ptr(self.colidx), _ptr(self.val), _ptr(self.chunk_row),
-                                   _ptr(self.chunk_start), _ptr(self.row_chunk_base), cb, ce, n, dim, row_begin,
-                                   row_end, _ptr(self.row_order(row_begin, row_end)), self.long_row(row_begin, row_end),
-                                   _ptr(X), _ptr(X0), float(alpha), float(beta), _ptr(out), _ptr(partial), _ptr(counters),
-                                   _stream()), "spmm layer")
+        args = (_ptr(self.rowptr), _ptr(self.colidx), _ptr(self.val), _ptr(self.chunk_row),
+                _ptr(self.chunk_start), _ptr(self.row_chunk_base), cb, ce, n, dim, row_begin,
+                row_end, _ptr(self.row_order(row_begin, row_end)), self.long_row(row_begin, row_end),
+                _ptr(X), _ptr(X0), float(alpha), float(beta), _ptr(out), _ptr(partial), _ptr(counters))
+        if src_mask is None:
+            check(lib().lgc_spmm_layer(*args, _stream()), "spmm layer")
+        else:
+            check(lib().lgc_spmm_layer_masked(*args, _ptr(_mask_ok(src_mask, n)), _stream()), "spmm layer (masked source)")
         return out
 
     def spmm_bcast(self, X: torch.Tensor, X0: Optional[torch.Tensor], alpha: float, beta: float,
@@ -262,22 +267,30 @@ class NormGraph:
         return hit
 
     def spmm_rows_bcast(self, X: torch.Tensor, X0: Optional[torch.Tensor], alpha: float, beta: float,
-                        peer_ptrs: Sequence[int], ranges: Sequence[tuple[int, int]]) -> None:
-        """One mixed launch over up to two row ranges, every finished row stored into all replicas."""
+                        peer_ptrs: Sequence[int], ranges: Sequence[tuple[int, int]],
+                        src_mask: Optional[torch.Tensor] = None) -> None:
+        """One mixed launch over up to two row ranges, every finished row stored into all replicas.  src_mask: as in spmm."""
         X = _req(X, torch.float32, "X")
         n, dim = self.n_nodes, int(X.shape[1])
         rows, long_row, ch = self.row_list(ranges)
         partial, counters = self._scr(dim)
         arr = (C.c_void_p * len(peer_ptrs))(*[C.c_void_p(p) for p in peer_ptrs])
-        check(lib().lgc_spmm_rows_bcast(_ptr(self.rowptr), _ptr(self.colidx), _ptr(self.val), _ptr(self.chunk_row),
-                                        _ptr(self.chunk_start), _ptr(self.row_chunk_base), ch[0][0], ch[0][1], ch[1][0],
-                                        ch[1][1], n, dim, _ptr(rows), int(rows.numel()), long_row, _ptr(X), _ptr(X0),
-                                        float(alpha), float(beta), arr, len(peer_ptrs), _ptr(partial), _ptr(counters),
-                                        _stream()), "spmm rows bcast")
+        args = (_ptr(self.rowptr), _ptr(self.colidx), _ptr(self.val), _ptr(self.chunk_row),
+                _ptr(self.chunk_start), _ptr(self.row_chunk_base), ch[0][0], ch[0][1], ch[1][0],
+                ch[1][1], n, dim, _ptr(rows), int(rows.numel()), long_row, _ptr(X), _ptr(X0),
+                float(alpha), float(beta), arr, len(peer_ptrs), _ptr(partial), _ptr(counters))
+        if src_mask is None:
+            check(lib().lgc_spmm_rows_bcast(*args, _stream()), "spmm rows bcast")
+        else:
+            check(lib().lgc_spmm_rows_bcast_masked(*args, _ptr(_mask_ok(src_mask, n)), _stream()),
+                  "spmm rows bcast (masked source)")
 
     def propagate_mean(self, X0: torch.Tensor, n_layers: int, out: Optional[torch.Tensor] = None,
-                       tmp: Optional[tuple[torch.Tensor, torch.Tensor]] = None, coop: Optional[bool] = None) -> torch.Tensor:
+                       tmp: Optional[tuple[torch.Tensor, torch.Tensor]] = None, coop: Optional[bool] = None,
+                       x0_row_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         """E = mean_l(A_hat^l X0), l = 0..n_layers (model/LightGCN/model.py:56-69).
+        x0_row_mask (see row_mask_words / row_mask_batch): X0 is zero outside the rows whose bit is set — the first layer
+        (the only one that reads X0 as its source) then skips the gathers of the zero rows; used for dL/dE in training.
         coop=True (or LGCNHS_COOP=1 for graphs with <= COOP_MAX_NNZ non-zeros): all layers in ONE cooperative launch with
         grid barriers between them.  Opt-in: measured on B200 (tools/coop_probe.py, profiles/r2_coop_probe.txt) the grid
         barriers cost more than the launches they replace at every configured shape."""
@@ -291,6 +304,14 @@ class NormGraph:
             tmp = (torch.empty_like(X0), torch.empty_like(X0))
         if coop is None:
             coop = 0 < self.nnz <= self.COOP_MAX_NNZ and n_layers >= 1 and os.environ.get("LGCNHS_COOP", "0") == "1"
+        if x0_row_mask is not None and n_layers >= 1:
+            partial, counters = self._scr(dim)
+            check(lib().lgc_propagate_mean_masked(_ptr(self.rowptr), _ptr(self.colidx), _ptr(self.val), _ptr(self.chunk_row),
+                                                  _ptr(self.chunk_start), _ptr(self.row_chunk_base), self.n_chunks, n, dim,
+                                                  int(n_layers), _ptr(self.row_order()), self.long_row(), _ptr(X0), _ptr(out),
+                                                  _ptr(tmp[0]), _ptr(tmp[1]), _ptr(partial), _ptr(counters),
+                                                  _ptr(_mask_ok(x0_row_mask, n)), _stream()), "propagate_mean (masked source)")
+            return out
         if coop:
             cu = self.coop_units()
             part = cu["partial"].get(dim)
@@ -317,6 +338,25 @@ class NormGraph:
 
     def layer_bytes_compulsory(self, dim: int) -> int:
         return self.nnz * 8 + (self.n_nodes + 1) * 4 + 2 * self.n_nodes * 4 * dim
+
+
+def row_mask_words(n_rows: int, device) -> torch.Tensor:
+    """An all-clear row mask for n_rows rows: int32 words, bit (r & 31) of word r >> 5 belongs to row r."""
+    return torch.zeros(((n_rows + 31) // 32 + 1,), dtype=torch.int32, device=device)
+
+
+def _mask_ok(mask: torch.Tensor, n_rows: int) -> torch.Tensor:
+    if mask.dtype != torch.int32 or not mask.is_cuda or not mask.is_contiguous() or mask.numel() * 32 < n_rows:
+        raise LgcnhsError("row mask: contiguous CUDA int32 words covering every row expected (row_mask_words)")
+    return mask
+
+
+def row_mask_batch(mask: torch.Tensor, users: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor, n_users: int,
+                   set_bits: bool) -> None:
+    """Set (or clear again) the bits of rows users[b], n_users + pos[b], n_users + neg[b]: the non-zero rows of dL/dE."""
+    check(lib().lgc_row_mask_batch(_ptr(mask), _ptr(_req(users, torch.int64, "users")), _ptr(_req(pos, torch.int64, "pos")),
+                                   _ptr(_req(neg, torch.int64, "neg")), int(users.numel()), int(n_users), 1 if set_bits else 0,
+                                   _stream()), "row mask batch")
 
 
 def probe_gather_gbs(n_rows: int, dim: int = 64, n_gathers: int = 32_000_000, reps: int = 5, device=None) -> dict:

@@ -38,7 +38,12 @@ class FusedBPRTrainer:
     RowPartitionedPropagation: fused SpMM + peer-store all-gather + device barrier, no NCCL call in the step); every
     rank evaluates the (tiny) BPR kernel on the same mini-batch; Adam runs only on the rows a rank owns and stores the
     updated rows into every rank's weight table over NVLink, followed by one device barrier.  The loss is replicated
-    (no reduction needed).  All ranks must draw the same mini-batches (same torch seed)."""
+    (no reduction needed).  All ranks must draw the same mini-batches (same torch seed).
+
+    Sparse first gradient layer: dL/dE has at most 3 * batch non-zero rows, so the first of the K gradient layers would
+    gather ~98 % exact zeros.  The step keeps a one-bit-per-node mask of the batch rows (lgc_row_mask_batch) and the first
+    layer skips the masked-out gathers (lgc_propagate_mean_masked / lgc_spmm_rows_bcast_masked): bit-identical gradients,
+    one of the 2K layers at the cost of its (colidx, val) stream.  LGCNHS_DENSE_BACKWARD=1 switches it off."""
 
     def __init__(self, model, train_adj_index: torch.Tensor, lr: float, eps_reg: float,
                  betas=(0.9, 0.999), adam_eps: float = 1e-8, graph: Optional[bool] = None, distributed: bool = False,
@@ -71,6 +76,8 @@ class FusedBPRTrainer:
             model.items_emb.weight.data = self.X0[self.U:]
         self.uw, self.iw = model.users_emb.weight, model.items_emb.weight
         self.gE, self.gX = z(), z()
+        self.sparse_backward = os.environ.get("LGCNHS_DENSE_BACKWARD", "0") != "1"
+        self.row_mask = ops.row_mask_words(self.N, dev)      # all clear between steps, like gE / gX
         self.exp_avg, self.exp_avg_sq = z(), z()
         self.lr, self.eps_reg, self.betas, self.adam_eps = lr, eps_reg, betas, adam_eps
         self.t = 0
@@ -137,11 +144,16 @@ class FusedBPRTrainer:
         X0, E = self.forward_embeddings()
         bpr = ops.bpr_fwd_bwd_det if self.deterministic else ops.bpr_fwd_bwd
         bpr(E, X0, self.U, self.M, users, pos, neg, self.eps_reg, self.gE, self.gX, loss_out=self.loss_dev)
-        # dL/dX0 = mean_l (A^T)^l dL/dE  +  regulariser rows
+        # dL/dX0 = mean_l (A^T)^l dL/dE  +  regulariser rows; dL/dE is non-zero on the batch rows only
+        mask = self.row_mask if self.sparse_backward and self.K >= 1 else None
+        if mask is not None:
+            ops.row_mask_batch(mask, users, pos, neg, self.U, True)
         if self.distributed:
-            gP = self.prop.propagate_mean(self.gE, self.K, result=1)
+            gP = self.prop.propagate_mean(self.gE, self.K, result=1, x0_row_mask=mask)
         else:
-            gP = self.gt.propagate_mean(self.gE, self.K, out=self.gP, tmp=(self.tmp0, self.tmp1))
+            gP = self.gt.propagate_mean(self.gE, self.K, out=self.gP, tmp=(self.tmp0, self.tmp1), x0_row_mask=mask)
+        if mask is not None:
+            ops.row_mask_batch(mask, users, pos, neg, self.U, False)
         if self.debug_keep_grad:            # tests only (eager steps): the dense dL/dX0 that Adam consumes as two operands
             self.grad_total = gP + self.gX
         ops.adam_hyper_step(self.step_dev, self.lr_dev, self.betas[0], self.betas[1], self.hyper_dev)

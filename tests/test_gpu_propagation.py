@@ -205,3 +205,75 @@ def test_cooperative_k_layer_kernel(dev, name, hub, dim, layers):
     assert int((cu["end"] - cu["start"]).max()) <= 128 and int((cu["end"] - cu["start"]).sum()) == g.nnz
     if hub:
         assert cu["n_split"] >= 1
+
+
+@pytest.mark.parametrize("name,hub,dim,frac", [("tiny", 0, 64, 0.2), ("small", 300, 64, 0.02), ("ml-100k", 943, 64, 0.02),
+                                               ("ml-100k", 943, 32, 0.05), ("ml-100k", 0, 64, 0.0), ("ml-100k", 0, 64, 1.0)])
+def test_masked_source_layer_is_bit_identical(dev, name, hub, dim, frac):
+    """Sparse-source SpMM (lgc_spmm_layer_masked / lgc_propagate_mean_masked): with X zero outside the masked rows the
+    result must be the one of the unmasked call, bit for bit — the skipped terms are exact zeros.  Also checked against
+    the oracle layer, and on the long-row (chunk) path through the hub item."""
+    from lgcnhs_b200 import ops
+    from lgcnhs_b200.ops import NormGraph
+
+    d, adj = make_graph(name, hub)
+    n = d.n_users + d.n_items
+    g = NormGraph(adj.to(dev), n)
+    gen = torch.Generator().manual_seed(7)
+    live = torch.rand(n, generator=gen) < frac
+    if hub:
+        live[d.n_users] = True                                  # the hub item itself is a live source of the user rows
+        live[: min(hub, d.n_users) : 7] = True                  # and some of the hub's sources are live
+    X = torch.randn(n, dim, generator=gen) * live[:, None].float()
+    mask = ops.row_mask_words(n, dev)
+    rows = torch.nonzero(live).flatten()
+    words = torch.zeros(mask.numel(), dtype=torch.int64)
+    words.index_add_(0, rows // 32, torch.ones_like(rows) << (rows % 32))
+    mask.copy_(torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32))
+    Xd = X.to(dev)
+    plain = g.spmm(Xd, Xd, 0.25, 1.0)
+    masked = g.spmm(Xd, Xd, 0.25, 1.0, src_mask=mask)
+    assert torch.equal(plain, masked)
+    out_p = g.propagate_mean(Xd, 3)
+    out_m = g.propagate_mean(Xd, 3, x0_row_mask=mask)
+    assert torch.equal(out_p, out_m)
+    # a row range (the multi-GPU partition's launch shape) through the row-list entry
+    a, b = n // 3, n - n // 5
+    y0 = torch.zeros_like(Xd)
+    y1 = torch.zeros_like(Xd)
+    g.spmm_rows_bcast(Xd, Xd, 1.0, 1.0, [y0.data_ptr()], [(a, b)])
+    g.spmm_rows_bcast(Xd, Xd, 1.0, 1.0, [y1.data_ptr()], [(a, b)], src_mask=mask)
+    assert torch.equal(y0, y1)
+
+
+def test_row_mask_batch_sets_and_clears(dev):
+    from lgcnhs_b200 import ops
+
+    U, M, B = 1000, 777, 300
+    gen = torch.Generator().manual_seed(3)
+    users = torch.randint(0, U, (B,), generator=gen).to(dev)
+    pos = torch.randint(0, M, (B,), generator=gen).to(dev)
+    neg = torch.randint(0, M, (B,), generator=gen).to(dev)
+    mask = ops.row_mask_words(U + M, dev)
+    ops.row_mask_batch(mask, users, pos, neg, U, True)
+    bits = ((mask.cpu().numpy().view(np.uint32)[:, None] >> np.arange(32, dtype=np.uint32)[None, :]) & 1).reshape(-1)[: U + M]
+    want = np.zeros(U + M, dtype=np.uint32)
+    want[users.cpu().numpy()] = 1
+    want[U + pos.cpu().numpy()] = 1
+    want[U + neg.cpu().numpy()] = 1
+    assert np.array_equal(bits, want)
+    ops.row_mask_batch(mask, users, pos, neg, U, False)
+    assert int(mask.abs().sum()) == 0
+
+
+def test_masked_source_rejects_dim_128(dev):
+    from lgcnhs_b200 import ops
+    from lgcnhs_b200._lib import LgcnhsError
+    from lgcnhs_b200.ops import NormGraph
+
+    d, adj = make_graph("tiny")
+    n = d.n_users + d.n_items
+    g = NormGraph(adj.to(dev), n)
+    X = torch.zeros(n, 128, device=dev)
+    with pytest.raises(LgcnhsError):
+        g.spmm(X, X, 1.0, 1.0, src_mask=ops.row_mask_words(n, dev))

@@ -157,3 +157,39 @@ def test_deterministic_training_is_bit_reproducible(dev):
         torch.cuda.synchronize()
         finals.append(t.X0.clone())
     assert torch.equal(finals[0], finals[1])
+
+
+def test_sparse_first_gradient_layer_equals_dense_backward(dev, monkeypatch):
+    """The masked first gradient layer (dL/dE is non-zero on the batch rows only) must leave the training trajectory
+    unchanged: same weights, bit for bit, as with LGCNHS_DENSE_BACKWARD=1 — eager steps and graph replays, and the mask is
+    all-clear again after every step."""
+    import _stub_const
+
+    _stub_const.install()
+    from lgcnhs_b200.synth import bipartite_adj, synth_shape
+    from lgcnhs_b200.trainer import FusedBPRTrainer
+    from model.LightGCN.model import LightGCN
+
+    d = synth_shape("ml-100k")
+    tr, _, _ = d.split()
+    adj = torch.from_numpy(bipartite_adj(d.n_users, d.users[tr], d.items[tr])).to(dev)
+    finals, losses = [], []
+    for dense in ("0", "1"):
+        monkeypatch.setenv("LGCNHS_DENSE_BACKWARD", dense)
+        torch.manual_seed(42)
+        m = LightGCN(d.n_users, d.n_items, 64, 3).to(dev)
+        t = FusedBPRTrainer(m, adj, lr=1e-2, eps_reg=1e-4, deterministic=True)
+        assert t.sparse_backward == (dense == "0")
+        g = torch.Generator().manual_seed(5)
+        ls = []
+        for s in range(5):
+            u = torch.randint(d.n_users, (256,), generator=g).to(dev)
+            p = torch.randint(d.n_items, (256,), generator=g).to(dev)
+            n = torch.randint(d.n_items, (256,), generator=g).to(dev)
+            ls.append(t.step(u, p, n).clone())
+            assert int(t.row_mask.abs().sum()) == 0
+        torch.cuda.synchronize()
+        finals.append(t.X0.clone())
+        losses.append(torch.stack(ls))
+    assert torch.equal(finals[0], finals[1])
+    assert torch.equal(losses[0], losses[1])
