@@ -42,8 +42,10 @@ class FusedBPRTrainer:
 
     Sparse first gradient layer: dL/dE has at most 3 * batch non-zero rows, so the first of the K gradient layers would
     gather ~98 % exact zeros.  The step keeps a one-bit-per-node mask of the batch rows (lgc_row_mask_batch) and the first
-    layer skips the masked-out gathers (lgc_propagate_mean_masked / lgc_spmm_rows_bcast_masked): bit-identical gradients,
-    one of the 2K layers at the cost of its (colidx, val) stream.  LGCNHS_DENSE_BACKWARD=1 switches it off."""
+    layer skips the masked-out gathers (lgc_propagate_mean_masked / lgc_spmm_rows_bcast_masked): bit-identical gradients.
+    Measured on B200 (tools/sparse_backward_bench.py): that layer 101 -> 81 us at the Amazon-Book shape (the (colidx, val)
+    stream and the per-row work remain), step 755 -> 745 us; on graphs below ~2 M non-zeros the two mask launches cost what
+    the layer saves, so it is used from 2 M non-zeros up (LGCNHS_DENSE_BACKWARD=1 / =0 forces it off / on)."""
 
     def __init__(self, model, train_adj_index: torch.Tensor, lr: float, eps_reg: float,
                  betas=(0.9, 0.999), adam_eps: float = 1e-8, graph: Optional[bool] = None, distributed: bool = False,
@@ -76,7 +78,7 @@ class FusedBPRTrainer:
             model.items_emb.weight.data = self.X0[self.U:]
         self.uw, self.iw = model.users_emb.weight, model.items_emb.weight
         self.gE, self.gX = z(), z()
-        self.sparse_backward = os.environ.get("LGCNHS_DENSE_BACKWARD", "0") != "1"
+        self._dense_env = os.environ.get("LGCNHS_DENSE_BACKWARD")
         self.row_mask = ops.row_mask_words(self.N, dev)      # all clear between steps, like gE / gX
         self.exp_avg, self.exp_avg_sq = z(), z()
         self.lr, self.eps_reg, self.betas, self.adam_eps = lr, eps_reg, betas, adam_eps
@@ -111,6 +113,7 @@ class FusedBPRTrainer:
         else:
             self.g, self.gt = graphs_for(train_adj_index, self.N)
             self.E, self.gP, self.tmp0, self.tmp1 = z(), z(), z(), z()
+        self.sparse_backward = (self.g.nnz >= 2_000_000) if self._dense_env is None else self._dense_env != "1"
         if graph is None:
             graph = os.environ.get("LGCNHS_NO_GRAPH", "0") != "1"
         self.use_graph = bool(graph)
