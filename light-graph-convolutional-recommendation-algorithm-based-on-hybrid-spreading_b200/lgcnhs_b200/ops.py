@@ -101,11 +101,14 @@ class NormGraph:
         deg = (self.rowptr[1:] - self.rowptr[:-1]).to(torch.int64)
         rows = torch.repeat_interleave(torch.arange(n, device=dev, dtype=torch.int64), deg)
         cols = self.colidx[:nnz].to(torch.int64)
-        order = torch.argsort(cols * n + rows)           # keyed by the old source, old targets ascending inside
+        # keyed by the old source, old targets ascending inside: own radix sort of the (source, target) keys; a value is
+        # ONE fp32 product of the two dinv factors (edge_val_kernel), so it is recomputed instead of permuted — same bits
+        keys = sort_u64(cols * n + rows, bits=max(1, (n * n - 1).bit_length()))
+        new_rows, new_cols = keys // n, keys % n
         t.colidx = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
         t.val = torch.empty(max(nnz, 1), dtype=torch.float32, device=dev)
-        t.colidx[:nnz] = rows[order].to(torch.int32)
-        t.val[:nnz] = self.val[:nnz][order]
+        t.colidx[:nnz] = new_cols.to(torch.int32)
+        t.val[:nnz] = self.dinv[new_rows] * self.dinv[new_cols]
         tdeg = torch.bincount(cols, minlength=n)
         rowptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
         torch.cumsum(tdeg, 0, out=rowptr[1:])

@@ -90,3 +90,29 @@ def test_unique_and_graph_converters_on_device(dev):
     back_cpu = graph.convertAdjMatrixToEdgeIndex(d.n_users, d.n_items, adj_cpu)
     back_dev = graph.convertAdjMatrixToEdgeIndex(d.n_users, d.n_items, adj_dev)
     assert torch.equal(back_dev.cpu(), back_cpu)
+
+
+def test_transposed_graph_matches_argsort_construction(dev):
+    """NormGraph.transposed() (own radix sort of the (source, target) keys, values recomputed as dinv x dinv) against the
+    plain construction: a stable argsort of the same keys and the PERMUTED values of the forward graph — integer arrays
+    and fp32 values bit-equal, on a non-symmetric graph."""
+    from lgcnhs_b200.ops import NormGraph
+
+    gen = torch.Generator().manual_seed(11)
+    n, e = 3000, 40000
+    src = torch.randint(0, n, (e,), generator=gen)
+    dst = (torch.rand(e, generator=gen) ** 2 * n).long().clamp(max=n - 1)      # skewed targets -> some long rows
+    key = torch.unique(src * n + dst)
+    ei = torch.stack([key // n, key % n]).to(dev)
+    g = NormGraph(ei, n)
+    t = g.transposed()
+    nnz = g.nnz
+    deg = (g.rowptr[1:] - g.rowptr[:-1]).to(torch.int64)
+    rows = torch.repeat_interleave(torch.arange(n, device=dev), deg)
+    cols = g.colidx[:nnz].to(torch.int64)
+    order = torch.argsort(cols * n + rows, stable=True)
+    assert torch.equal(t.colidx[:nnz], rows[order].to(torch.int32))
+    assert torch.equal(t.val[:nnz], g.val[:nnz][order])
+    want_ptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    want_ptr[1:] = torch.cumsum(torch.bincount(cols, minlength=n), 0)
+    assert torch.equal(t.rowptr.to(torch.int64), want_ptr)
