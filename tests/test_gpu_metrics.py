@@ -184,3 +184,51 @@ def test_metrics_dropin_modules_match_reference_golden(dev):
     assert np.allclose(diversity.getDiversityMetrics(rec, deg, A, 10), z["diversity"], atol=1e-5)
     assert abs(diversity.calHammingDistance(rec, 10) - z["diversity"][0]) <= 1e-5
     assert abs(diversity.calInternalSimilarity(rec, deg, A, 10) - z["diversity"][1]) <= 1e-5
+
+
+def test_multi_k_evaluation_matches_per_call_metrics(dev, tmp_path):
+    """evaluationMetrics.py:43-96 as one batched call (lgcnhs_b200.evaluate_lists): several (model, k) list sets — dict and
+    array inputs, duplicated test rows — against the independent NumPy formulas (the reference's, pinned to its outputs in
+    test_cpu_host_logic.py) and against the drop-in metrics modules called the way evaluationMetrics.py calls them."""
+    import _stub_const
+
+    _stub_const.install()
+    import pandas as pd
+
+    import _metrics_numpy as MN
+    from lgcnhs_b200.evaluate_lists import evaluate_lists
+    from lgcnhs_b200.synth import synth_shape
+    from metrics.accurate import getAccurateMetrics
+    from metrics.diversity import getDiversityMetrics
+
+    d = synth_shape("small")
+    tr, va, te = d.split()
+    U, M = d.n_users, d.n_items
+    frame = lambda idx: pd.DataFrame({"user_id": d.users[idx], "item_id": d.items[idx]})  # noqa: E731
+    train_df, val_df = frame(tr), frame(va)
+    test_df = pd.concat([frame(te), frame(te[:50])])          # duplicated test rows: the reference keeps them (len(items))
+    gen = np.random.default_rng(5)
+    lists = {}
+    for name in ("HybridS", "LightGCN"):
+        for k in (5, 10, 30):
+            rec = np.stack([gen.choice(M, size=k, replace=False) for _ in range(U)])
+            lists[(name, k)] = {u: rec[u].tolist() for u in range(U)} if name == "HybridS" else rec
+    frames = evaluate_lists(U, M, train_df, val_df, test_df, lists, save_path=str(tmp_path) + "/")
+    assert sorted(frames) == [5, 10, 30] and all(list(f["Model"]) == ["HybridS", "LightGCN"] for f in frames.values())
+    tv = np.r_[tr, va]
+    A = S.interaction_matrix(U, M, d.users[tv], d.items[tv])
+    deg = {i: int(c) for i, c in enumerate(A.sum(0)) if c > 0}
+    test_dict = {}
+    for u, i in zip(test_df["user_id"].tolist(), test_df["item_id"].tolist()):
+        test_dict.setdefault(u, []).append(i)
+    for (name, k), val in lists.items():
+        rec = np.asarray([val[u] for u in range(U)]) if isinstance(val, dict) else val
+        row = frames[k][frames[k]["Model"] == name].iloc[0]
+        got = [row["P"], row["R"], row["F1"], row["NDCG"], row["H"], row["I"]]
+        p, r, f1, n = MN.accurate_metrics(test_dict, rec, k)
+        H, I = MN.diversity_metrics(rec, deg, A, k)
+        assert np.allclose(got, [p, r, f1, n, H, I], atol=1e-5), (name, k, got, [p, r, f1, n, H, I])
+        rt = torch.from_numpy(rec)
+        assert np.allclose(got[:4], getAccurateMetrics(test_dict, rt, k), atol=1e-12)
+        assert np.allclose(got[4:], getDiversityMetrics(rt, deg, A, k), atol=1e-12)
+    assert os.path.exists(str(tmp_path) + "/model_evaluation_results_30.csv")
