@@ -211,3 +211,24 @@ def test_partition_cost_weighting_and_metric_sums():
     assert m["precision"] == 1.0 and m["recall"] == 0.25 and m["ndcg"] == 0.4
     assert m["f1"] == round(2 * 1.0 * 0.25 / 1.25, 5)
     assert m["H"] == round(1 - 180.0 / (10 * 9 * 3), 5) and m["I"] == round(54.0 / (10 * 3 * 2), 5)
+
+
+def test_evaluate_lists_input_forms():
+    """Host side of the multi-k evaluation driver (evaluationMetrics.py:43-96): the saved dict{uid: ids} format, arrays and
+    tensors give the same (U, k) id matrix in user order; short or ragged inputs fail loudly."""
+    from lgcnhs_b200.evaluate_lists import lists_to_tensor
+
+    U, k = 6, 3
+    rec = np.arange(U * 5).reshape(U, 5)
+    as_dict = {u: rec[u].tolist() for u in reversed(range(U))}          # insertion order must not matter
+    cpu = torch.device("cpu")
+    want = torch.from_numpy(rec[:, :k])
+    assert torch.equal(lists_to_tensor(as_dict, U, k, cpu), want)
+    assert torch.equal(lists_to_tensor(rec, U, k, cpu), want)
+    assert torch.equal(lists_to_tensor(torch.from_numpy(rec).int(), U, k, cpu), want)
+    with pytest.raises(ValueError):
+        lists_to_tensor({u: rec[u, :2].tolist() for u in range(U)}, U, k, cpu)
+    with pytest.raises(ValueError):
+        lists_to_tensor(rec[:-1], U, k, cpu)
+    with pytest.raises(KeyError):
+        lists_to_tensor({u: rec[u].tolist() for u in range(U - 1)}, U, k, cpu)
