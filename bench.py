@@ -702,7 +702,7 @@ def training_leg(dev, steps: int, warmup: int, rank: int = 0, world: int = 1):
             "step_no_reuse_gbs": round(gbs, 1),
             "what": "device mini-batch + negative sampling kernel, then ONE CUDA graph per step: 2K fused SpMM layers (fwd + grad) + fused BPR fwd/bwd scatter + Adam (device-resident bias corrections); no host sync",
             "eval_ms": round(ms_eval, 2), "eval_users_per_s": round(d.n_users / (ms_eval * 1e-3), 1), "eval_e2e": eval_e2e,
-            "eval_what": "ONE fused kernel: layer-0 score tiles (packed fp32 FMA) + train-pair fill(-1024) + top-20 over all 91 599 items; the U x M score matrix is never written; the mask CSR of the train pairs is built once per graph (2nd evaluation timed)"}
+            "eval_what": "ONE fused kernel + a candidate merge: layer-0 score tiles on the tensor cores (tcgen05 kind::tf32, 3xTF32 split) + train-pair fill(-1024) + top-20 over all 91 599 items; the U x M score matrix is never written; the mask CSR of the train pairs is built once per graph (2nd evaluation timed)"}
 
 
 _REAL_STDOUT = None
